@@ -1,0 +1,179 @@
+/*
+ * mtm_b200 — C ABI of the B200-native hard-assignment EM hot path for mixtures of
+ * linear-Gaussian state-space models.
+ *
+ * Drop-in boundary for the numerics of burkh4rt/Multimodal-Trajectory-Modeling's
+ *   framework/marginalizable_mixture_model.py   (MMM)  class MMLinGaussSS_marginalizable
+ *   framework/marginalizable_state_space_model.py (SSM) mm / CC / multivariate_normal_log_likelihood
+ * Each entry point cites the reference interface it replaces.  The reference has no FFI of
+ * its own (it is pure Python); the binding a maintainer would add is the ctypes stub shown
+ * in INTEGRATION.md (and shipped in multimodal-trajectory-modeling_b200/_capi.py).
+ *
+ * Conventions
+ *  - every pointer named *_dev is DEVICE memory owned by the caller (e.g. a torch tensor's
+ *    data_ptr()); the library never frees or retains it beyond the call, except the data
+ *    set bound with mtm_set_data, which must stay alive while bound;
+ *  - trajectories: states z (T, n, d) and observations x (T, n, l), C-contiguous float64,
+ *    time-major, missing = any non-finite value (NaN or +-inf)  [MMM:60-63, SSM:770];
+ *  - parameters: (n_c, mtm_param_stride(d,l)) float64 rows
+ *        [pi | m (d) | S (d,d) | A (d,d) | Gamma (d,d) | H (d,l) | Lambda (l,l)], row-major,
+ *    i.e. the reference attributes cluster_propensities / init_state_means / init_state_covs /
+ *    transition_matrices / transition_covs / measurement_matrices / measurement_covs
+ *    [MMM:83-125];
+ *  - assignments: int32 on the device (the reference holds int64 from np.argmax; the host
+ *    layer widens);
+ *  - every function returns 0 on success, <0 on error (message: mtm_last_error); numerical
+ *    trouble is NOT an error code but a bit in mtm_fit_info.status / the status word, so
+ *    the host can emulate the reference's exceptions [MMM:1439-1442, 1463-1464];
+ *  - work is enqueued on the handle's CUDA stream; only calls that return host values
+ *    (mtm_em_fit, mtm_mstep, mtm_score, mtm_estep when info != NULL, mtm_fp64_peak)
+ *    synchronise that stream.  One handle per (process, device); calls on one handle must
+ *    be serialised by the caller (the reference class is not re-entrant either).
+ */
+#ifndef MTM_B200_H
+#define MTM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTM_ABI_VERSION 1
+#define MTM_MAX_DIM 8        /* largest supported d and l */
+#define MTM_MAX_CLUSTERS 64  /* largest n_c of one model */
+
+/* status bits (mtm_fit_info.status, mtm_estep_info.status) */
+#define MTM_STATUS_NONFINITE 1   /* a covariance pivot was NaN/inf: the reference's det/solve raise
+                                    LinAlgError("Array must not contain infs or NaNs") [SSM:771-773] */
+#define MTM_STATUS_SINGULAR 2    /* an exactly zero pivot: the reference's solve raises "singular" */
+#define MTM_STATUS_EMPTY_FIT 4   /* a regression had no usable rows: lstsq / Ridge raise [MMM:1194,1226] */
+#define MTM_STATUS_CHOL_FAIL 8   /* normal equations not positive definite in the M-step */
+
+/* exit codes of the EM loop [MMM:1310-1366] */
+#define MTM_EXIT_RUNNING 0
+#define MTM_EXIT_CONVERGED 1  /* an E-step changed no assignment            [MMM:1342-1345] */
+#define MTM_EXIT_GUARD 2      /* min cluster size <= 3 after an E-step       [MMM:1346-1356] */
+#define MTM_EXIT_EXHAUSTED 3  /* n_steps E-steps done                        [MMM:1340]      */
+#define MTM_EXIT_GUARD0 4     /* min cluster size <= 3 before the first M-step: nothing ran [MMM:1328-1336] */
+#define MTM_EXIT_ERROR 5      /* a numerical failure on which the reference raises (status != 0): the loop
+                                 stops at that step so the host can raise the same exception */
+
+typedef struct mtm_handle mtm_handle;
+
+/* a data set in device memory; z_dev == NULL means "all hidden states missing"
+ * (the observation-only route, MMM:997-1048, 1125-1165) */
+typedef struct {
+    const double *z_dev;
+    const double *x_dev;
+    int64_t n;
+    int32_t T;
+    int32_t d;
+    int32_t l;
+    int32_t reserved;
+} mtm_data;
+
+typedef struct {
+    int64_t n_switches;  /* assignments changed by this E-step (global if a communicator is attached
+                            and the call all-reduces; mtm_estep itself is local) */
+    int64_t min_count;   /* smallest cluster size after the E-step (local) */
+    int32_t status;      /* MTM_STATUS_* bits */
+    int32_t reserved;
+} mtm_estep_info;
+
+typedef struct {
+    int32_t exit_code;   /* MTM_EXIT_* */
+    int32_t n_e_steps;   /* E-steps executed; the reference's reported "i" is n_e_steps-1 on convergence */
+    int32_t status;      /* MTM_STATUS_* bits accumulated over the fit */
+    int32_t n_m_steps;   /* M-steps executed */
+    int64_t last_switches;
+    int64_t min_count;
+} mtm_fit_info;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int mtm_abi_version(void);
+/* stream: a cudaStream_t (NULL = legacy default stream) */
+int mtm_create(int device, void *stream, mtm_handle **out);
+int mtm_destroy(mtm_handle *h);
+int mtm_set_stream(mtm_handle *h, void *stream);
+/* message of the last error on this handle (h == NULL: last error of mtm_create) */
+const char *mtm_last_error(mtm_handle *h);
+
+/* ---- layout helpers ---------------------------------------------------------------------- */
+int mtm_param_stride(int d, int l); /* 1 + d + 3 d^2 + d l + l^2   (85 at d=l=4) */
+int mtm_stats_stride(int d, int l); /* sufficient statistics per cluster (106 at d=l=4), see DESIGN.md */
+
+/* ---- resident training set  [MMM:45-81: ctor stores states/observations] ---------------- */
+int mtm_set_data(mtm_handle *h, const mtm_data *data);
+
+/* ---- E-step ---------------------------------------------------------------------------------
+ * Replaces, in one launch: conditional_log_likelihoods[_first_T0_steps] for every cluster
+ * (MMM:439-530 -> SSM mm/CC/multivariate_normal_log_likelihood, SSM:259-364, 728-773),
+ * mle_cluster_assignment (MMM:724-791: linear-domain argmax of pi_c exp(ll_c), first max wins,
+ * NaN wins; optional probs and prenormalised log-probs), E_step's switch count (MMM:1235-1252),
+ * and — with data->z_dev == NULL — observed_condl_log_lik_first_T0_steps /
+ * observations_mle_cluster_assignment (MMM:997-1165).
+ *   data           NULL = the resident set
+ *   T0             time cutoff, clamped to data->T   (MMM:473, 1026)
+ *   assign_dev     (n) int32, nullable.  If count_switches != 0 it is read as the old assignment
+ *                  first and info->n_switches counts the changes.
+ *   ll/probs/prenorm_dev  (n_c, n) float64 outputs, each nullable
+ *   info           host struct, nullable; when given the call synchronises the stream      */
+int mtm_estep(mtm_handle *h, const mtm_data *data, const double *params_dev, int n_c, int T0,
+              int32_t *assign_dev, int count_switches, double *ll_dev, double *probs_dev,
+              double *prenorm_dev, mtm_estep_info *info);
+
+/* ---- scores -----------------------------------------------------------------------------------
+ * out_host[0] = Q  = sum_i log pi_{a_i} + ll[a_i, i] with a = argmax   (e_complete_data_log_lik, MMM:579-624)
+ * out_host[1] = LL = sum_i log sum_c pi_c exp(ll[c,i])                  (model_log_likelihood,   MMM:626-666)
+ * Sums are all-reduced over the attached communicator.  Synchronises. */
+int mtm_score(mtm_handle *h, const mtm_data *data, const double *params_dev, int n_c, double *out_host,
+              int32_t *status_host);
+
+/* ---- M-step -------------------------------------------------------------------------------------
+ * mtm_mstats: per-cluster sufficient statistics of the resident set under assign_dev
+ *   (restates M_step's masked gathers as moments, MMM:1254-1308); stats_dev (n_c, stats_stride),
+ *   local to this rank (no collective).
+ * mtm_finalize: parameters from (all-reduced) statistics: pi = N_c / n_total (MMM:1261-1263),
+ *   m, S (np.cov, ddof=1; MMM:1267-1270), (A, Gamma) and (H, Lambda) by regress / regress_alpha
+ *   (MMM:1167-1233): alpha <= 2 eps -> least squares, else ridge (X'X + alpha I) B = X'Y; residual
+ *   covariance mean-subtracted with N-1.
+ * mtm_mstep: mstats -> all-reduce over the attached communicator -> finalize; writes
+ *   params_dev; info (nullable) receives min_count and status.  Synchronises if info != NULL. */
+int mtm_mstats(mtm_handle *h, const int32_t *assign_dev, int n_c, double *stats_dev);
+int mtm_finalize(mtm_handle *h, const double *stats_dev, int n_c, int d, int l, int64_t n_total,
+                 double alpha, double *params_dev, int32_t *status_dev);
+int mtm_mstep(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, double *params_dev,
+              mtm_estep_info *info);
+
+/* ---- EM fit --------------------------------------------------------------------------------------
+ * train (MMM:1310-1366) on the resident set, loop resident on the device:
+ *   guard -> M -> { E ; stop if 0 switches ; guard ; M } for at most n_steps E-steps.
+ * assign_dev (n) int32 in/out: initial assignment in, final assignment out.
+ * params_dev (n_c, param_stride) out: parameters of the last executed M-step (untouched on GUARD0).
+ * switches_host (nullable, capacity switches_cap): n_switches after every E-step.
+ * With a communicator attached every rank calls this on its shard; one all-reduce of
+ * [statistics | n_switches] per iteration; all ranks return identical params/info. */
+int mtm_em_fit(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assign_dev,
+               double *params_dev, mtm_fit_info *info, int64_t *switches_host, int switches_cap);
+
+/* ---- data-parallel sharding (one process per GPU) ----------------------------------------------
+ * The library opens the NCCL that is already loaded in the process (libnccl.so.2).  Rank 0 obtains
+ * an id with mtm_comm_unique_id and distributes the 128 bytes by any means (the Python host uses
+ * torch.distributed); then every rank calls mtm_comm_init.  Collective calls: mtm_comm_init,
+ * mtm_mstep, mtm_em_fit, mtm_score, mtm_comm_destroy. */
+int mtm_comm_unique_id(void *id128_out);
+int mtm_comm_init(mtm_handle *h, const void *id128, int world_size, int rank);
+int mtm_comm_destroy(mtm_handle *h);
+
+/* ---- measurement ---------------------------------------------------------------------------------
+ * DFMA-saturating micro-kernel: FP64 peak of this device in TFLOP/s (FMA = 2 flop), best of `reps`,
+ * CUDA-event timed.  Denominator of the FP64 roofline (MEASURED_PEAKS.json has none). */
+int mtm_fp64_peak(mtm_handle *h, int reps, double *tflops_out);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t mtm_launch_count(mtm_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTM_B200_H */

@@ -1,0 +1,544 @@
+// C ABI of mtm_b200 (see include/mtm_b200.h): handle, scratch, the stream-resident EM loop and
+// the NCCL plumbing.  No C++ exception crosses the boundary.
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+
+using namespace mtm;
+
+// ---- minimal NCCL surface, resolved at run time from the libnccl.so.2 already in the process ----
+extern "C" {
+typedef struct ncclComm *ncclComm_t;
+typedef struct {
+    char internal[128];
+} ncclUniqueId;
+}
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+bool load_nccl(std::string &err) {
+    if (g_nccl.ok) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) {
+        err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+        return false;
+    }
+#define MTM_SYM(field, name)                                                   \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.lib, name)); \
+    if (!g_nccl.field) {                                                       \
+        err = std::string("NCCL symbol missing: ") + name;                     \
+        return false;                                                          \
+    }
+    MTM_SYM(GetUniqueId, "ncclGetUniqueId")
+    MTM_SYM(CommInitRank, "ncclCommInitRank")
+    MTM_SYM(AllReduce, "ncclAllReduce")
+    MTM_SYM(CommDestroy, "ncclCommDestroy")
+    MTM_SYM(GetErrorString, "ncclGetErrorString")
+#undef MTM_SYM
+    g_nccl.ok = true;
+    return true;
+}
+std::string g_create_error;
+}  // namespace
+
+struct mtm_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    mtm_data data{};
+    bool has_data = false;
+    Ctrl *d_ctrl = nullptr;
+    Ctrl *h_ctrl = nullptr;  // pinned
+    double *d_partials = nullptr;
+    size_t partials_cap = 0;
+    double *d_statsbuf = nullptr;
+    size_t statsbuf_cap = 0;
+    double *d_score = nullptr;  // [2 outputs | partials]
+    size_t score_cap = 0;
+    unsigned long long *d_counts = nullptr;  // MTM_MAX_CLUSTERS
+    unsigned long long *h_counts = nullptr;  // pinned
+    long long *d_hist = nullptr;
+    int hist_cap = 0;
+    double *h_pin = nullptr;  // small pinned scratch (16 doubles)
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    std::string err;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(mtm_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define MTM_CUDA(h, expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) return fail(h, -2, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), \
+                                           __FILE__, __LINE__, #expr);                         \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <class T>
+int ensure(mtm_handle *h, T *&ptr, size_t &cap, size_t need) {
+    if (need <= cap) return 0;
+    if (ptr) MTM_CUDA(h, cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&ptr), need * sizeof(T)));
+    cap = need;
+    return 0;
+}
+
+int check_dims(mtm_handle *h, const mtm_data *dt, int n_c) {
+    if (!dt || !dt->x_dev) return fail(h, -1, "no data: bind a set with mtm_set_data or pass one");
+    if (dt->d < 1 || dt->d > MTM_MAX_DIM || dt->l < 1 || dt->l > MTM_MAX_DIM)
+        return fail(h, -1, "dimensions d=%d l=%d outside [1, %d]", dt->d, dt->l, MTM_MAX_DIM);
+    if (dt->T < 1 || dt->n < 1) return fail(h, -1, "empty data set (T=%d, n=%lld)", dt->T, (long long)dt->n);
+    if (n_c < 1 || n_c > MTM_MAX_CLUSTERS) return fail(h, -1, "n_c=%d outside [1, %d]", n_c, MTM_MAX_CLUSTERS);
+    if ((dt->d % 2 == 0 && dt->z_dev && (reinterpret_cast<uintptr_t>(dt->z_dev) & 15)) ||
+        (dt->l % 2 == 0 && (reinterpret_cast<uintptr_t>(dt->x_dev) & 15)))
+        return fail(h, -1, "z_dev / x_dev must be 16-byte aligned");
+    return 0;
+}
+
+int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n_c, int T0, int32_t *assign,
+                  int count_switches, double *ll, double *probs, double *prenorm, unsigned long long *counts,
+                  double *score_partials, int check_done, int *grid_out) {
+    EStepArgs a{};
+    a.z = dt->z_dev;
+    a.x = dt->x_dev;
+    a.n = dt->n;
+    a.T = dt->T;
+    a.T0 = T0 < 1 ? 1 : (T0 > dt->T ? dt->T : T0);
+    a.d = dt->d;
+    a.l = dt->l;
+    a.params = params;
+    a.n_c = n_c;
+    a.assign = assign;
+    a.count_switches = count_switches;
+    a.ll = ll;
+    a.probs = probs;
+    a.prenorm = prenorm;
+    a.ctrl = h->d_ctrl;
+    a.counts = counts;
+    a.score_partials = score_partials;
+    a.check_done = check_done;
+    const int grid = estep_grid(dt->n, h->sm_count);
+    if (grid_out) *grid_out = grid;
+    const size_t smem = estep_smem(n_c, a.T0, a.d, a.l);
+    if (smem > 200 * 1024) return fail(h, -1, "E-step shared memory %zu B too large (n_c * T0 too big)", smem);
+    MTM_CUDA(h, launch_estep(a, grid, smem, h->stream));
+    h->launches += 1;
+    return 0;
+}
+
+int allreduce_stats(mtm_handle *h, double *buf, size_t count) {
+    if (!h->comm) return 0;
+    const int r = g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
+    if (r != 0) return fail(h, -3, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+    return 0;
+}
+
+// statistics of the resident set under `assign` -> h->d_statsbuf [n_c*sstride | n_switches | n_local],
+// all-reduced over the communicator
+int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done, int with_switches) {
+    const mtm_data &dt = h->data;
+    const int sstride = stats_stride(dt.d, dt.l);
+    const int n_vals = n_c * sstride;
+    const int grid = stats_grid(dt.n, h->sm_count);
+    const size_t smem = stats_smem(n_c, dt.d, dt.l);
+    if (smem > 220 * 1024)
+        return fail(h, -1, "statistics kernel needs %zu B of shared memory (n_c=%d, d=%d, l=%d): too large", smem, n_c,
+                    dt.d, dt.l);
+    if (int rc = ensure(h, h->d_partials, h->partials_cap, (size_t)2 * grid * n_vals)) return rc;
+    if (int rc = ensure(h, h->d_statsbuf, h->statsbuf_cap, (size_t)n_vals + 2)) return rc;
+    StatsArgs s{};
+    s.z = dt.z_dev;
+    s.x = dt.x_dev;
+    s.n = dt.n;
+    s.T = dt.T;
+    s.d = dt.d;
+    s.l = dt.l;
+    s.assign = assign;
+    s.n_c = n_c;
+    s.partials = h->d_partials;
+    s.ctrl = h->d_ctrl;
+    s.check_done = check_done;
+    MTM_CUDA(h, launch_stats(s, grid, h->stream));
+    MTM_CUDA(h, launch_stats_reduce(h->d_partials, grid, n_vals, h->d_statsbuf, h->d_ctrl, check_done,
+                                    with_switches ? &h->d_ctrl->n_switches : nullptr, (double)dt.n, h->stream));
+    h->launches += 2;
+    return allreduce_stats(h, h->d_statsbuf, (size_t)n_vals + 2);
+}
+
+int enqueue_finalize(mtm_handle *h, int n_c, double alpha, double *params, int mode, int n_steps) {
+    const mtm_data &dt = h->data;
+    FinalizeArgs f{};
+    f.stats = h->d_statsbuf;
+    f.n_c = n_c;
+    f.d = dt.d;
+    f.l = dt.l;
+    f.n_total = dt.n;
+    f.alpha = alpha;
+    f.params = params;
+    f.ctrl = h->d_ctrl;
+    f.mode = mode;
+    f.n_steps = n_steps;
+    f.switch_hist = h->d_hist;
+    MTM_CUDA(h, launch_finalize(f, h->d_statsbuf + (size_t)n_c * stats_stride(dt.d, dt.l), h->stream));
+    h->launches += 1;
+    return 0;
+}
+
+int read_ctrl(mtm_handle *h) {
+    MTM_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mtm_abi_version(void) { return MTM_ABI_VERSION; }
+
+const char *mtm_last_error(mtm_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mtm_param_stride(int d, int l) { return param_stride(d, l); }
+int mtm_stats_stride(int d, int l) { return stats_stride(d, l); }
+
+int mtm_create(int device, void *stream, mtm_handle **out) {
+    if (!out) return fail(nullptr, -1, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, -2, "no CUDA device available (%s): mtm_b200 has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return fail(nullptr, -1, "device %d out of range [0, %d)", device, count);
+    mtm_handle *h = new (std::nothrow) mtm_handle();
+    if (!h) return fail(nullptr, -4, "out of host memory");
+    h->device = device;
+    h->stream = reinterpret_cast<cudaStream_t>(stream);
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(nullptr, -2, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    if (prop.major < 10) {
+        delete h;
+        return fail(nullptr, -2, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    }
+    h->sm_count = prop.multiProcessorCount;
+    bool ok = cudaMalloc(reinterpret_cast<void **>(&h->d_ctrl), sizeof(Ctrl)) == cudaSuccess &&
+              cudaMallocHost(reinterpret_cast<void **>(&h->h_ctrl), sizeof(Ctrl)) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void **>(&h->d_counts), sizeof(unsigned long long) * MTM_MAX_CLUSTERS) ==
+                  cudaSuccess &&
+              cudaMallocHost(reinterpret_cast<void **>(&h->h_counts), sizeof(unsigned long long) * MTM_MAX_CLUSTERS) ==
+                  cudaSuccess &&
+              cudaMallocHost(reinterpret_cast<void **>(&h->h_pin), sizeof(double) * 16) == cudaSuccess &&
+              cudaMemset(h->d_ctrl, 0, sizeof(Ctrl)) == cudaSuccess;
+    if (!ok) {
+        const char *msg = cudaGetErrorString(cudaGetLastError());
+        mtm_destroy(h);
+        return fail(nullptr, -2, "allocation of control blocks failed: %s", msg);
+    }
+    *out = h;
+    return 0;
+}
+
+int mtm_destroy(mtm_handle *h) {
+    if (!h) return 0;
+    DeviceGuard g(h->device);
+    if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+    cudaFree(h->d_ctrl);
+    cudaFreeHost(h->h_ctrl);
+    cudaFree(h->d_partials);
+    cudaFree(h->d_statsbuf);
+    cudaFree(h->d_score);
+    cudaFree(h->d_counts);
+    cudaFreeHost(h->h_counts);
+    cudaFree(h->d_hist);
+    cudaFreeHost(h->h_pin);
+    delete h;
+    return 0;
+}
+
+int mtm_set_stream(mtm_handle *h, void *stream) {
+    if (!h) return -1;
+    h->stream = reinterpret_cast<cudaStream_t>(stream);
+    return 0;
+}
+
+int mtm_set_data(mtm_handle *h, const mtm_data *data) {
+    if (!h) return -1;
+    if (!data) {
+        h->has_data = false;
+        return 0;
+    }
+    if (int rc = check_dims(h, data, 1)) return rc;
+    if (!data->z_dev) return fail(h, -1, "the resident training set needs hidden states (z_dev)");
+    h->data = *data;
+    h->has_data = true;
+    return 0;
+}
+
+int mtm_estep(mtm_handle *h, const mtm_data *data, const double *params_dev, int n_c, int T0, int32_t *assign_dev,
+              int count_switches, double *ll_dev, double *probs_dev, double *prenorm_dev, mtm_estep_info *info) {
+    if (!h) return -1;
+    const mtm_data *dt = data ? data : (h->has_data ? &h->data : nullptr);
+    if (int rc = check_dims(h, dt, n_c)) return rc;
+    if (!params_dev) return fail(h, -1, "params_dev is NULL");
+    DeviceGuard g(h->device);
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    MTM_CUDA(h, cudaMemsetAsync(h->d_counts, 0, sizeof(unsigned long long) * MTM_MAX_CLUSTERS, h->stream));
+    if (int rc = enqueue_estep(h, dt, params_dev, n_c, T0, assign_dev, count_switches && assign_dev, ll_dev, probs_dev,
+                               prenorm_dev, h->d_counts, nullptr, 0, nullptr))
+        return rc;
+    if (info) {
+        MTM_CUDA(h, cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(unsigned long long) * n_c, cudaMemcpyDeviceToHost,
+                                    h->stream));
+        if (int rc = read_ctrl(h)) return rc;
+        unsigned long long mn = ~0ull;
+        for (int c = 0; c < n_c; ++c) mn = h->h_counts[c] < mn ? h->h_counts[c] : mn;
+        info->n_switches = (int64_t)h->h_ctrl->n_switches;
+        info->min_count = (int64_t)mn;
+        info->status = h->h_ctrl->status;
+        info->reserved = 0;
+    }
+    return 0;
+}
+
+int mtm_score(mtm_handle *h, const mtm_data *data, const double *params_dev, int n_c, double *out_host,
+              int32_t *status_host) {
+    if (!h || !out_host) return -1;
+    const mtm_data *dt = data ? data : (h->has_data ? &h->data : nullptr);
+    if (int rc = check_dims(h, dt, n_c)) return rc;
+    DeviceGuard g(h->device);
+    const int grid = estep_grid(dt->n, h->sm_count);
+    if (int rc = ensure(h, h->d_score, h->score_cap, (size_t)2 + 2 * grid)) return rc;
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    if (int rc = enqueue_estep(h, dt, params_dev, n_c, dt->T, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                               h->d_score + 2, 0, nullptr))
+        return rc;
+    MTM_CUDA(h, launch_score_reduce(h->d_score + 2, grid, h->d_score, h->stream));
+    h->launches += 1;
+    if (int rc = allreduce_stats(h, h->d_score, 2)) return rc;
+    MTM_CUDA(h, cudaMemcpyAsync(h->h_pin, h->d_score, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (int rc = read_ctrl(h)) return rc;
+    out_host[0] = h->h_pin[0];
+    out_host[1] = h->h_pin[1];
+    if (status_host) *status_host = h->h_ctrl->status;
+    return 0;
+}
+
+int mtm_mstats(mtm_handle *h, const int32_t *assign_dev, int n_c, double *stats_dev) {
+    if (!h) return -1;
+    if (!h->has_data) return fail(h, -1, "no resident data set (mtm_set_data)");
+    if (int rc = check_dims(h, &h->data, n_c)) return rc;
+    if (!assign_dev || !stats_dev) return fail(h, -1, "NULL argument");
+    DeviceGuard g(h->device);
+    // local statistics only: temporarily detach the communicator
+    ncclComm_t keep = h->comm;
+    h->comm = nullptr;
+    const int rc = enqueue_stats(h, assign_dev, n_c, 0, 0);
+    h->comm = keep;
+    if (rc) return rc;
+    const size_t n_vals = (size_t)n_c * stats_stride(h->data.d, h->data.l);
+    MTM_CUDA(h, cudaMemcpyAsync(stats_dev, h->d_statsbuf, n_vals * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+int mtm_finalize(mtm_handle *h, const double *stats_dev, int n_c, int d, int l, int64_t n_total, double alpha,
+                 double *params_dev, int32_t *status_dev) {
+    if (!h || !stats_dev || !params_dev) return -1;
+    if (d < 1 || d > MTM_MAX_DIM || l < 1 || l > MTM_MAX_DIM || n_c < 1 || n_c > MTM_MAX_CLUSTERS)
+        return fail(h, -1, "bad dimensions");
+    DeviceGuard g(h->device);
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    FinalizeArgs f{};
+    f.stats = stats_dev;
+    f.n_c = n_c;
+    f.d = d;
+    f.l = l;
+    f.n_total = n_total;
+    f.alpha = alpha;
+    f.params = params_dev;
+    f.ctrl = h->d_ctrl;
+    f.mode = 0;
+    MTM_CUDA(h, launch_finalize(f, nullptr, h->stream));
+    h->launches += 1;
+    if (status_dev)
+        MTM_CUDA(h, cudaMemcpyAsync(status_dev, &h->d_ctrl->status, sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+int mtm_mstep(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, double *params_dev,
+              mtm_estep_info *info) {
+    if (!h) return -1;
+    if (!h->has_data) return fail(h, -1, "no resident data set (mtm_set_data)");
+    if (int rc = check_dims(h, &h->data, n_c)) return rc;
+    if (!assign_dev || !params_dev) return fail(h, -1, "NULL argument");
+    DeviceGuard g(h->device);
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    if (int rc = enqueue_stats(h, assign_dev, n_c, 0, 0)) return rc;
+    if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 0, 0)) return rc;
+    if (info) {
+        if (int rc = read_ctrl(h)) return rc;
+        info->n_switches = 0;
+        info->min_count = h->h_ctrl->min_count;
+        info->status = h->h_ctrl->status;
+        info->reserved = 0;
+    }
+    return 0;
+}
+
+int mtm_em_fit(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assign_dev, double *params_dev,
+               mtm_fit_info *info, int64_t *switches_host, int switches_cap) {
+    if (!h) return -1;
+    if (!h->has_data) return fail(h, -1, "no resident data set (mtm_set_data)");
+    if (int rc = check_dims(h, &h->data, n_c)) return rc;
+    if (!assign_dev || !params_dev || !info) return fail(h, -1, "NULL argument");
+    if (n_steps < 0) return fail(h, -1, "n_steps < 0");
+    DeviceGuard g(h->device);
+    const mtm_data &dt = h->data;
+    if (n_steps > h->hist_cap) {
+        if (h->d_hist) MTM_CUDA(h, cudaFree(h->d_hist));
+        h->d_hist = nullptr;
+        h->hist_cap = 0;
+        MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->d_hist), sizeof(long long) * n_steps));
+        h->hist_cap = n_steps;
+    }
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    // guard + first M-step (MMM:1328-1337)
+    if (int rc = enqueue_stats(h, assign_dev, n_c, 0, 0)) return rc;
+    if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 1, n_steps)) return rc;
+    // { E ; stop if 0 switches ; guard ; M }: enqueued in batches, the kernels themselves stop
+    // working once the device-side `done` flag is up; the host only polls between batches
+    const int batch = ((double)dt.n * n_c < 2e6) ? 16 : 2;
+    int issued = 0;
+    if (int rc = read_ctrl(h)) return rc;
+    while (!h->h_ctrl->done && issued < n_steps) {
+        const int nb = (n_steps - issued < batch) ? (n_steps - issued) : batch;
+        for (int b = 0; b < nb; ++b) {
+            if (int rc = enqueue_estep(h, &dt, params_dev, n_c, dt.T, assign_dev, 1, nullptr, nullptr, nullptr, nullptr,
+                                       nullptr, 1, nullptr))
+                return rc;
+            if (int rc = enqueue_stats(h, assign_dev, n_c, 1, 1)) return rc;
+            if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 1, n_steps)) return rc;
+        }
+        issued += nb;
+        if (int rc = read_ctrl(h)) return rc;
+    }
+    const Ctrl &c = *h->h_ctrl;
+    info->exit_code = c.exit_code;
+    info->n_e_steps = c.n_e_steps;
+    info->status = c.status;
+    info->n_m_steps = c.n_m_steps;
+    info->last_switches = c.last_switches;
+    info->min_count = c.min_count;
+    if (switches_host && switches_cap > 0 && c.n_e_steps > 0) {
+        const int m = c.n_e_steps < switches_cap ? c.n_e_steps : switches_cap;
+        static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+        MTM_CUDA(h, cudaMemcpyAsync(switches_host, h->d_hist, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, h->stream));
+        MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int mtm_comm_unique_id(void *id128_out) {
+    std::string err;
+    if (!id128_out) return -1;
+    if (!load_nccl(err)) return fail(nullptr, -3, "%s", err.c_str());
+    ncclUniqueId id;
+    const int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, -3, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    memcpy(id128_out, &id, sizeof(id));
+    return 0;
+}
+
+int mtm_comm_init(mtm_handle *h, const void *id128, int world_size, int rank) {
+    if (!h || !id128) return -1;
+    std::string err;
+    if (!load_nccl(err)) return fail(h, -3, "%s", err.c_str());
+    if (h->comm) return fail(h, -1, "a communicator is already attached");
+    DeviceGuard g(h->device);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    const int r = g_nccl.CommInitRank(&h->comm, world_size, id, rank);
+    if (r != 0) {
+        h->comm = nullptr;
+        return fail(h, -3, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    }
+    h->world = world_size;
+    h->rank = rank;
+    return 0;
+}
+
+int mtm_comm_destroy(mtm_handle *h) {
+    if (!h) return -1;
+    if (h->comm && g_nccl.ok) {
+        DeviceGuard g(h->device);
+        cudaStreamSynchronize(h->stream);
+        g_nccl.CommDestroy(h->comm);
+    }
+    h->comm = nullptr;
+    h->world = 1;
+    h->rank = 0;
+    return 0;
+}
+
+int mtm_fp64_peak(mtm_handle *h, int reps, double *tflops_out) {
+    if (!h || !tflops_out) return -1;
+    DeviceGuard g(h->device);
+    MTM_CUDA(h, run_fp64_peak(reps < 1 ? 1 : reps, h->sm_count, h->stream, tflops_out));
+    h->launches += (reps < 1 ? 1 : reps) + 2;
+    return 0;
+}
+
+int64_t mtm_launch_count(mtm_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

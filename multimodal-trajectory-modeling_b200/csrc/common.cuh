@@ -1,0 +1,91 @@
+// Shared declarations of the mtm_b200 library (internal; the public surface is include/mtm_b200.h).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/mtm_b200.h"
+
+namespace mtm {
+
+constexpr int kEThreads = 128;  // E-step: one thread per trajectory, 4 warps per block
+constexpr int kSThreads = 128;  // statistics: one thread per trajectory, tile = block
+
+// Device-resident control block of the EM loop: written by the kernels, polled by the host.
+struct Ctrl {
+    int32_t done;       // loop finished: every later kernel of the enqueued batch returns at once
+    int32_t exit_code;  // MTM_EXIT_*
+    int32_t n_e_steps;
+    int32_t n_m_steps;
+    int32_t status;     // MTM_STATUS_* bits
+    int32_t pad;
+    unsigned long long n_switches;  // accumulated by the E-step kernel, consumed by finalize
+    long long last_switches;
+    long long min_count;
+};
+
+struct EStepArgs {
+    const double *z;  // (T, n, d) or nullptr
+    const double *x;  // (T, n, l)
+    int64_t n;
+    int T, T0, d, l;
+    const double *params;  // (n_c, stride)
+    int n_c;
+    int32_t *assign;       // nullable
+    int count_switches;
+    double *ll, *probs, *prenorm;  // nullable (n_c, n)
+    Ctrl *ctrl;                    // never null
+    unsigned long long *counts;    // (n_c) cluster sizes after the E-step, nullable
+    double *score_partials;        // nullable: (grid, 2) block sums of Q and LL terms
+    int check_done;                // honour ctrl->done (EM loop) or not (stand-alone calls)
+};
+
+struct StatsArgs {
+    const double *z, *x;
+    int64_t n;
+    int T, d, l;
+    const int32_t *assign;
+    int n_c;
+    double *partials;  // (grid, n_c, sstride, 2): block sums as (hi, lo) double-double pairs
+    const Ctrl *ctrl;
+    int check_done;
+};
+
+struct FinalizeArgs {
+    const double *stats;  // (n_c, sstride)
+    int n_c, d, l;
+    int64_t n_total;
+    double alpha;
+    double *params;  // (n_c, pstride) out
+    Ctrl *ctrl;
+    int mode;  // 0: plain M-step (always write); 1: EM-loop step (decide converged / guard / continue)
+    int n_steps;
+    long long *switch_hist;  // nullable
+};
+
+// launchers (one translation unit per kernel family so that nvcc can build them in parallel)
+cudaError_t launch_estep(const EStepArgs &a, int grid, size_t smem, cudaStream_t s);
+int estep_grid(int64_t n, int sm_count);
+size_t estep_smem(int n_c, int T0, int d, int l);
+
+cudaError_t launch_stats(const StatsArgs &a, int grid, cudaStream_t s);
+int stats_grid(int64_t n, int sm_count);
+size_t stats_smem(int n_c, int d, int l);
+// out (n_vals + 2): reduced statistics, then [n_switches of the preceding E-step, local n]
+cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, const Ctrl *ctrl,
+                                int check_done, const unsigned long long *n_switches_src, double n_local,
+                                cudaStream_t s);
+// tail (nullable) = the two trailing slots of the all-reduced statistics buffer
+cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStream_t s);
+cudaError_t launch_counts(const int32_t *assign, int64_t n, int n_c, unsigned long long *counts, cudaStream_t s);
+cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, cudaStream_t s);
+cudaError_t run_fp64_peak(int reps, int sm_count, cudaStream_t s, double *tflops);
+
+__host__ __device__ inline int param_stride(int d, int l) { return 1 + d + 3 * d * d + d * l + l * l; }
+// [N | n0, sum z (d), sum zz' (d(d+1)/2) | n1, sum u (2d), sum uu' (d(2d+1)) | n2, sum w (d+l), sum ww' ((d+l)(d+l+1)/2)]
+__host__ __device__ inline int stats_stride(int d, int l) {
+    const int D = d + l;
+    return 1 + (1 + d + d * (d + 1) / 2) + (1 + 2 * d + d * (2 * d + 1)) + (1 + D + D * (D + 1) / 2);
+}
+
+}  // namespace mtm

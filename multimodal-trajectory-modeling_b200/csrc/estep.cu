@@ -1,0 +1,208 @@
+// Kernel 1 (joint) and kernel 3 (measurement-only): E-step of the hard-assignment EM.
+//
+// One thread per trajectory, looping over the clusters; per cluster the thread runs the
+// register-resident sequential filter of filter.cuh, then forms L_c = pi_c * exp(ll_c) in the
+// linear domain and keeps the running argmax with numpy's rules (first maximum wins, the first
+// NaN wins), exactly like mle_cluster_assignment (framework/marginalizable_mixture_model.py:
+// 760-771).  The epilogue optionally writes ll / probs / prenorm (:775-791), counts assignment
+// switches (E_step, :1235-1252) and cluster sizes, and accumulates the block sums of
+// Q and LL terms (:579-666) in a fixed order.
+//
+// Memory: for a fixed time step the 32 lanes of a warp read 32 consecutive trajectories, i.e.
+// 32*d*8 contiguous bytes of z and 32*l*8 of x (16-byte vector loads, read-only path).  A
+// trajectory is streamed from HBM once per E-step: the n_c-1 later cluster passes of the same
+// thread hit L1/L2.  Parameters (n_c x 85 doubles at d=l=4) sit in shared memory and are read
+// as warp-uniform broadcasts.
+#include "common.cuh"
+#include "filter.cuh"
+
+namespace mtm {
+
+template <int D_, int L_, bool HAS_Z>
+__global__ void __launch_bounds__(kEThreads) estep_kernel(const EStepArgs a) {
+    using DM = Dims<D_, L_>;
+    const DM dm{a.d, a.l};
+    if (a.check_done && a.ctrl->done) return;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int stride = dm.stride();
+    double *s_par = reinterpret_cast<double *>(smem_raw);                 // n_c * stride
+    double *s_logpi = s_par + a.n_c * stride;                             // n_c
+    uint32_t *s_fin = reinterpret_cast<uint32_t *>(s_logpi + a.n_c);      // n_c * T0
+    unsigned int *s_cnt = s_fin + a.n_c * a.T0;                           // n_c
+    __shared__ double s_red[2][kEThreads / 32];
+    __shared__ unsigned int s_sw;
+
+    const int tid = threadIdx.x;
+    for (int k = tid; k < a.n_c * stride; k += kEThreads) s_par[k] = a.params[k];
+    for (int k = tid; k < a.n_c; k += kEThreads) s_cnt[k] = 0;
+    if (tid == 0) s_sw = 0;
+    __syncthreads();
+    for (int c = tid; c < a.n_c; c += kEThreads) {
+        s_logpi[c] = log(s_par[c * stride]);
+        mean_finite_masks(dm, s_par + c * stride, a.T0, s_fin + c * a.T0);
+    }
+    __syncthreads();
+
+    const int64_t n = a.n;
+    const int64_t n_tiles = (n + kEThreads - 1) / kEThreads;
+    const int64_t zs = n * dm.d(), xs = n * dm.l();
+    double q_acc = 0.0, l_acc = 0.0;
+    unsigned int sw_acc = 0;
+    int bad = 0;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i_raw = tile * kEThreads + tid;
+        const bool valid = i_raw < n;
+        const int64_t i = valid ? i_raw : n - 1;  // clamp: the tail lanes compute and discard
+        const double *z_i = HAS_Z ? a.z + i * dm.d() : nullptr;
+        const double *x_i = a.x + i * dm.l();
+
+        double best = 0.0, best_ll = 0.0, sum_l = 0.0;
+        int arg = 0;
+        for (int c = 0; c < a.n_c; ++c) {
+            const double ll = filter_eval<DM, HAS_Z>(dm, z_i, zs, x_i, xs, a.T0, s_par + c * stride,
+                                                     s_fin + c * a.T0, bad);
+            const double lc = s_par[c * stride] * exp(ll);
+            if (valid) {
+                if (a.ll) a.ll[(int64_t)c * n + i] = ll;
+                if (a.prenorm) a.prenorm[(int64_t)c * n + i] = s_logpi[c] + ll;
+                if (a.probs) a.probs[(int64_t)c * n + i] = lc;
+            }
+            sum_l += lc;
+            // np.argmax: strict > keeps the first maximum; a NaN beats everything, the first NaN stays
+            const bool take = (c == 0) || (!(best != best) && (lc > best || lc != lc));
+            if (take) {
+                best = lc;
+                best_ll = ll;
+                arg = c;
+            }
+        }
+        if (valid) {
+            if (a.probs) {
+                for (int c = 0; c < a.n_c; ++c) {
+                    const int64_t o = (int64_t)c * n + i;
+                    a.probs[o] = a.probs[o] / sum_l;
+                }
+            }
+            if (a.assign) {
+                if (a.count_switches) sw_acc += (a.assign[i] != arg) ? 1u : 0u;
+                a.assign[i] = arg;
+            }
+            q_acc += s_logpi[arg] + best_ll;
+            l_acc += log(sum_l);
+        }
+        if (a.counts) {
+            for (int c = 0; c < a.n_c; ++c) {
+                const unsigned int m = __ballot_sync(0xffffffffu, valid && arg == c);
+                if ((tid & 31) == 0 && m) atomicAdd(&s_cnt[c], (unsigned int)__popc(m));
+            }
+        }
+    }
+
+    // block epilogue: integer counters by atomics (exact, order-free), fp64 sums in a fixed order
+    if (bad) atomicOr(&a.ctrl->status, bad);
+    if (a.count_switches) {
+        MTM_UNROLL
+        for (int o = 16; o > 0; o >>= 1) sw_acc += __shfl_xor_sync(0xffffffffu, sw_acc, o);
+        if ((tid & 31) == 0 && sw_acc) atomicAdd(&s_sw, sw_acc);
+    }
+    if (a.score_partials) {
+        MTM_UNROLL
+        for (int o = 16; o > 0; o >>= 1) {
+            q_acc += __shfl_xor_sync(0xffffffffu, q_acc, o);
+            l_acc += __shfl_xor_sync(0xffffffffu, l_acc, o);
+        }
+        if ((tid & 31) == 0) {
+            s_red[0][tid >> 5] = q_acc;
+            s_red[1][tid >> 5] = l_acc;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (a.count_switches && s_sw) atomicAdd(&a.ctrl->n_switches, (unsigned long long)s_sw);
+        if (a.score_partials) {
+            double q = 0.0, l = 0.0;
+            for (int w = 0; w < kEThreads / 32; ++w) {
+                q += s_red[0][w];
+                l += s_red[1][w];
+            }
+            a.score_partials[2 * blockIdx.x] = q;
+            a.score_partials[2 * blockIdx.x + 1] = l;
+        }
+    }
+    if (a.counts)
+        for (int c = tid; c < a.n_c; c += kEThreads)
+            if (s_cnt[c]) atomicAdd(&a.counts[c], (unsigned long long)s_cnt[c]);
+}
+
+// fixed-order sum of the per-block (Q, LL) partials
+__global__ void score_reduce_kernel(const double *__restrict__ partials, int grid, double *out2) {
+    __shared__ double s[2][256];
+    double q = 0.0, l = 0.0;
+    for (int b = threadIdx.x; b < grid; b += 256) {
+        q += partials[2 * b];
+        l += partials[2 * b + 1];
+    }
+    s[0][threadIdx.x] = q;
+    s[1][threadIdx.x] = l;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s[0][threadIdx.x] += s[0][threadIdx.x + o];
+            s[1][threadIdx.x] += s[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out2[0] = s[0][0];
+        out2[1] = s[1][0];
+    }
+}
+
+size_t estep_smem(int n_c, int T0, int d, int l) {
+    return (size_t)n_c * param_stride(d, l) * 8 + (size_t)n_c * 8 + (size_t)n_c * T0 * 4 + (size_t)n_c * 4 + 16;
+}
+
+int estep_grid(int64_t n, int sm_count) {
+    const int64_t tiles = (n + kEThreads - 1) / kEThreads;
+    // enough blocks for every SM to hold its resident set several times over, so that the static
+    // tile striding balances; never more blocks than tiles
+    const int64_t cap = (int64_t)sm_count * 32;
+    return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
+template <int D_, int L_>
+static cudaError_t launch_dl(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
+    if (a.z) {
+        auto k = estep_kernel<D_, L_, true>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, kEThreads, smem, s>>>(a);
+    } else {
+        auto k = estep_kernel<D_, L_, false>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, kEThreads, smem, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_estep(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
+#define MTM_CASE(DD, LL) \
+    if (a.d == DD && a.l == LL) return launch_dl<DD, LL>(a, grid, smem, s);
+    MTM_CASE(4, 4)
+    MTM_CASE(2, 4)
+    MTM_CASE(2, 3)
+    MTM_CASE(1, 1)
+    MTM_CASE(3, 3)
+    MTM_CASE(2, 2)
+    MTM_CASE(5, 3)
+#undef MTM_CASE
+    return launch_dl<0, 0>(a, grid, smem, s);  // generic run-time dimensions
+}
+
+cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, cudaStream_t s) {
+    score_reduce_kernel<<<1, 256, 0, s>>>(partials, grid, out2);
+    return cudaGetLastError();
+}
+
+}  // namespace mtm

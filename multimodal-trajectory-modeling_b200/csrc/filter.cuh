@@ -1,0 +1,397 @@
+// Per-(trajectory, cluster) marginal log-likelihood of a linear-Gaussian state-space model in
+// prediction-error (sequential conditioning) form, register resident, fp64.
+//
+// Replaces the arithmetic of the reference's
+//   statespace.mm / CC  (framework/marginalizable_state_space_model.py:259-364) and
+//   multivariate_normal_log_likelihood (:728-773)
+// without ever forming the dense (d+l)T covariance: the reference itself checks that the dense
+// joint density equals the step-wise generative one (:993-1002).
+//
+// Row-vector convention (:8-16):  z_1 ~ N(m, S),  z_{t+1} = z_t A + N(0, Gamma),  x_t = z_t H + N(0, Lambda).
+//
+// For each time step t the thread holds the Gaussian of z_t given everything already conditioned
+// on, (mu, P).  Present coordinates of z_t are conditioned on one scalar at a time (an LDL'
+// factorisation of the present sub-block, one pivot per scalar); then the predictive of x_t,
+// (mu H, P H, H' P H + Lambda), is formed and its present coordinates are conditioned on the same
+// way; then (mu, P) <- (mu A, A' P A + Gamma).  Each pivot s with innovation v contributes
+// v^2 / s to the quadratic form and s to the determinant; missing coordinates contribute nothing
+// (gain 0), which is exactly the reference's sub-setting of mean and covariance.
+//
+// A coordinate counts as present iff (y - mean) is finite with `mean` the UNCONDITIONAL stacked
+// mean of the reference (:769-770) — so +-inf data and coordinates whose model mean is NaN are
+// both "missing".  The per-(cluster, t) finiteness of that mean is precomputed as a bit mask.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mtm_b200.h"
+
+namespace mtm {
+
+// Compile-time (D_, L_ > 0: loops unrolled, state in registers) or run-time (D_ == 0: generic
+// fallback for any d, l <= MTM_MAX_DIM, state in local memory) dimensions behind one source.
+template <int D_, int L_>
+struct Dims {
+    static constexpr bool kStatic = (D_ > 0);
+    static constexpr int DM = kStatic ? D_ : MTM_MAX_DIM;
+    static constexpr int LM = kStatic ? L_ : MTM_MAX_DIM;
+    int d_rt, l_rt;
+    __host__ __device__ __forceinline__ int d() const { return kStatic ? D_ : d_rt; }
+    __host__ __device__ __forceinline__ int l() const { return kStatic ? L_ : l_rt; }
+    __host__ __device__ __forceinline__ int stride() const {
+        return 1 + d() + 3 * d() * d() + d() * l() + l() * l();
+    }
+};
+
+#define MTM_UNROLL _Pragma("unroll")
+
+__device__ __forceinline__ bool finite_bits(double y) {
+    // exponent field != all ones; integer pipe, keeps the FP64 pipe free
+    return (__double2hiint(y) & 0x7ff00000) != 0x7ff00000;
+}
+
+// 1/s to ~1 ulp: hardware seed + two Newton steps (4 DFMA) instead of the IEEE division's slow path.
+// s = 0 -> NaN, s = +-inf -> NaN, NaN -> NaN: all of these are flagged by the caller.
+__device__ __forceinline__ double fast_rcp(double s) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+    double e = fma(-s, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-s, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// pointers into one packed parameter row [pi | m | S | A | G | H | Lam]
+template <class DM>
+struct ParamView {
+    const double *pi, *m, *S, *A, *G, *H, *Lam;
+    __device__ __forceinline__ ParamView(const DM &dm, const double *row) {
+        const int d = dm.d(), l = dm.l();
+        pi = row;
+        m = row + 1;
+        S = m + d;
+        A = S + d * d;
+        G = A + d * d;
+        H = G + d * d;
+        Lam = H + d * l;
+    }
+};
+
+template <class DM>
+struct FilterState {
+    double mu[DM::DM];
+    double P[DM::DM][DM::DM];  // symmetric; only i <= j is kept
+    double q;                  // sum v^2 / s
+    double mant;               // running product of pivots, mantissa part (sign kept)
+    int expo;                  // ... and its binary exponent
+    int k;                     // number of present scalars
+    int bad;                   // MTM_STATUS_* bits
+};
+
+// element (i, j) of a symmetric matrix stored in its upper triangle
+template <class M>
+__device__ __forceinline__ double symget(const M &P, int i, int j) {
+    return i <= j ? P[i][j] : P[j][i];
+}
+
+template <class DM>
+__device__ __forceinline__ void filter_init(const DM &dm, FilterState<DM> &f, const ParamView<DM> &p) {
+    const int d = dm.d();
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            f.mu[i] = p.m[i];
+            MTM_UNROLL
+            for (int j = i; j < DM::DM; ++j)
+                if (j < d) f.P[i][j] = p.S[i * d + j];
+        }
+    }
+    f.q = 0.0;
+    f.mant = 1.0;
+    f.expo = 0;
+    f.k = 0;
+    f.bad = 0;
+}
+
+// (mu, P) <- (mu A, A' P A + Gamma)     [SSM:62-64 for P, :312-314 for mu]
+template <class DM>
+__device__ __forceinline__ void filter_propagate(const DM &dm, FilterState<DM> &f, const ParamView<DM> &p) {
+    const int d = dm.d();
+    double nmu[DM::DM];
+    double PA[DM::DM][DM::DM];
+    MTM_UNROLL
+    for (int j = 0; j < DM::DM; ++j) {
+        if (j < d) {
+            double s = 0.0;
+            MTM_UNROLL
+            for (int i = 0; i < DM::DM; ++i)
+                if (i < d) s = fma(f.mu[i], p.A[i * d + j], s);
+            nmu[j] = s;
+        }
+    }
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            MTM_UNROLL
+            for (int j = 0; j < DM::DM; ++j) {
+                if (j < d) {
+                    double s = 0.0;
+                    MTM_UNROLL
+                    for (int a = 0; a < DM::DM; ++a)
+                        if (a < d) s = fma(symget(f.P, i, a), p.A[a * d + j], s);
+                    PA[i][j] = s;
+                }
+            }
+        }
+    }
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            f.mu[i] = nmu[i];
+            MTM_UNROLL
+            for (int j = i; j < DM::DM; ++j) {
+                if (j < d) {
+                    double s = p.G[i * d + j];
+                    MTM_UNROLL
+                    for (int a = 0; a < DM::DM; ++a)
+                        if (a < d) s = fma(p.A[a * d + i], PA[a][j], s);
+                    f.P[i][j] = s;
+                }
+            }
+        }
+    }
+}
+
+// condition on the present coordinates of z_t (noise-free observations of state coordinates)
+template <class DM>
+__device__ __forceinline__ void filter_condition_z(const DM &dm, FilterState<DM> &f, const double (&zt)[DM::DM],
+                                                   uint32_t finmask) {
+    const int d = dm.d();
+    MTM_UNROLL
+    for (int j = 0; j < DM::DM; ++j) {
+        if (j < d) {
+            const double y = zt[j];
+            const bool obs = finite_bits(y) && ((finmask >> j) & 1u);
+            const double s = f.P[j][j];
+            f.bad |= (obs && !finite_bits(s)) ? MTM_STATUS_NONFINITE : 0;
+            f.bad |= (obs && s == 0.0) ? MTM_STATUS_SINGULAR : 0;
+            const double r = obs ? fast_rcp(s) : 0.0;
+            const double v = obs ? (y - f.mu[j]) : 0.0;
+            f.q = fma(v * v, r, f.q);
+            f.mant *= obs ? s : 1.0;
+            f.k += obs ? 1 : 0;
+            double col[DM::DM];
+            MTM_UNROLL
+            for (int i = 0; i < DM::DM; ++i)
+                if (i < d) col[i] = symget(f.P, i, j);
+            MTM_UNROLL
+            for (int i = 0; i < DM::DM; ++i) {
+                if (i < d) {
+                    const double g = col[i] * r;
+                    f.mu[i] = fma(g, v, f.mu[i]);
+                    MTM_UNROLL
+                    for (int b = i; b < DM::DM; ++b)
+                        if (b < d) f.P[i][b] = fma(-g, col[b], f.P[i][b]);
+                }
+            }
+            // the conditioned coordinate is now known exactly
+            MTM_UNROLL
+            for (int i = 0; i < DM::DM; ++i) {
+                if (i < d) {
+                    if (i <= j) f.P[i][j] = obs ? 0.0 : f.P[i][j];
+                    else f.P[j][i] = obs ? 0.0 : f.P[j][i];
+                }
+            }
+            f.mu[j] = obs ? y : f.mu[j];
+        }
+    }
+}
+
+// predictive of x_t and conditioning on its present coordinates   [SSM:161-166, 217-222, 337-339]
+template <class DM>
+__device__ __forceinline__ void filter_condition_x(const DM &dm, FilterState<DM> &f, const ParamView<DM> &p,
+                                                   const double (&xt)[DM::LM], uint32_t finmask) {
+    const int d = dm.d(), l = dm.l();
+    double mux[DM::LM];
+    double C[DM::DM][DM::LM];   // Cov(z_t, x_t | past) = P H
+    double Sx[DM::LM][DM::LM];  // Var(x_t | past) = H' P H + Lambda, upper triangle
+    MTM_UNROLL
+    for (int b = 0; b < DM::LM; ++b) {
+        if (b < l) {
+            double s = 0.0;
+            MTM_UNROLL
+            for (int i = 0; i < DM::DM; ++i)
+                if (i < d) s = fma(f.mu[i], p.H[i * l + b], s);
+            mux[b] = s;
+        }
+    }
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            MTM_UNROLL
+            for (int b = 0; b < DM::LM; ++b) {
+                if (b < l) {
+                    double s = 0.0;
+                    MTM_UNROLL
+                    for (int a = 0; a < DM::DM; ++a)
+                        if (a < d) s = fma(symget(f.P, i, a), p.H[a * l + b], s);
+                    C[i][b] = s;
+                }
+            }
+        }
+    }
+    MTM_UNROLL
+    for (int a = 0; a < DM::LM; ++a) {
+        if (a < l) {
+            MTM_UNROLL
+            for (int b = a; b < DM::LM; ++b) {
+                if (b < l) {
+                    double s = p.Lam[a * l + b];
+                    MTM_UNROLL
+                    for (int i = 0; i < DM::DM; ++i)
+                        if (i < d) s = fma(p.H[i * l + a], C[i][b], s);
+                    Sx[a][b] = s;
+                }
+            }
+        }
+    }
+    MTM_UNROLL
+    for (int j = 0; j < DM::LM; ++j) {
+        if (j < l) {
+            const double y = xt[j];
+            const bool obs = finite_bits(y) && ((finmask >> j) & 1u);
+            const double s = Sx[j][j];
+            f.bad |= (obs && !finite_bits(s)) ? MTM_STATUS_NONFINITE : 0;
+            f.bad |= (obs && s == 0.0) ? MTM_STATUS_SINGULAR : 0;
+            const double r = obs ? fast_rcp(s) : 0.0;
+            const double v = obs ? (y - mux[j]) : 0.0;
+            f.q = fma(v * v, r, f.q);
+            f.mant *= obs ? s : 1.0;
+            f.k += obs ? 1 : 0;
+            MTM_UNROLL
+            for (int i = 0; i < DM::DM; ++i) {
+                if (i < d) {
+                    const double g = C[i][j] * r;
+                    f.mu[i] = fma(g, v, f.mu[i]);
+                    MTM_UNROLL
+                    for (int a = i; a < DM::DM; ++a)
+                        if (a < d) f.P[i][a] = fma(-g, C[a][j], f.P[i][a]);
+                    MTM_UNROLL
+                    for (int b = j + 1; b < DM::LM; ++b)
+                        if (b < l) C[i][b] = fma(-g, Sx[j][b], C[i][b]);
+                }
+            }
+            MTM_UNROLL
+            for (int a = j + 1; a < DM::LM; ++a) {
+                if (a < l) {
+                    const double g = Sx[j][a] * r;
+                    mux[a] = fma(g, v, mux[a]);
+                    MTM_UNROLL
+                    for (int b = a; b < DM::LM; ++b)
+                        if (b < l) Sx[a][b] = fma(-g, Sx[j][b], Sx[a][b]);
+                }
+            }
+        }
+    }
+}
+
+// keep the running determinant in range: move the binary exponent of `mant` into `expo`
+template <class DM>
+__device__ __forceinline__ void filter_rescale(FilterState<DM> &f) {
+    const int hi = __double2hiint(f.mant);
+    const int e = (hi >> 20) & 0x7ff;
+    if (e != 0 && e != 0x7ff) {  // normal number (zero / subnormal / inf / NaN are left alone)
+        f.expo += e - 1022;
+        f.mant = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(f.mant));
+    }
+}
+
+// -1/2 (k log 2 pi + log det) - 1/2 q.  A negative determinant gives NaN like the reference's
+// log((2 pi)^k det) (:771-772); no present coordinate gives -0.0.
+template <class DM>
+__device__ __forceinline__ double filter_finish(const FilterState<DM> &f) {
+    const double logdet = fma((double)f.expo, 0.6931471805599453094, log(f.mant));
+    return -0.5 * fma((double)f.k, 1.8378770664093454836, logdet) - 0.5 * f.q;
+}
+
+// vector load of N doubles (16-byte loads when the row size allows; pointers are 16-byte aligned
+// by the ABI contract when N is even)
+template <int NM>
+__device__ __forceinline__ void load_row(const double *__restrict__ p, double (&v)[NM], int n_rt, bool is_static) {
+    if (is_static && (NM % 2 == 0)) {
+        MTM_UNROLL
+        for (int k = 0; k < NM / 2; ++k) {
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(p) + k);
+            v[2 * k] = t.x;
+            v[2 * k + 1] = t.y;
+        }
+    } else {
+        MTM_UNROLL
+        for (int k = 0; k < NM; ++k)
+            if (k < n_rt) v[k] = __ldg(p + k);
+    }
+}
+
+// One full evaluation.  z_i / x_i point at step 0 of trajectory i; zs / xs = step strides in doubles.
+// fin[t] = bit mask of finite unconditional means at step t: bits [0, d) for z, [16, 16 + l) for x.
+template <class DM, bool HAS_Z>
+__device__ __forceinline__ double filter_eval(const DM &dm, const double *__restrict__ z_i, int64_t zs,
+                                              const double *__restrict__ x_i, int64_t xs, int T0,
+                                              const double *prow, const uint32_t *fin, int &bad) {
+    const ParamView<DM> p(dm, prow);
+    FilterState<DM> f;
+    filter_init(dm, f, p);
+    double zt[DM::DM], xt[DM::LM];
+    if (HAS_Z) load_row<DM::DM>(z_i, zt, dm.d(), DM::kStatic);
+    load_row<DM::LM>(x_i, xt, dm.l(), DM::kStatic);
+    for (int t = 0; t < T0; ++t) {
+        // software pipeline: issue the loads of step t+1 before the arithmetic of step t
+        double zn[DM::DM], xn[DM::LM];
+        const int tn = (t + 1 < T0) ? t + 1 : t;
+        if (HAS_Z) load_row<DM::DM>(z_i + tn * zs, zn, dm.d(), DM::kStatic);
+        load_row<DM::LM>(x_i + tn * xs, xn, dm.l(), DM::kStatic);
+        const uint32_t fm = fin[t];
+        if (t > 0) filter_propagate(dm, f, p);
+        if (HAS_Z) filter_condition_z(dm, f, zt, fm & 0xffffu);
+        filter_condition_x(dm, f, p, xt, fm >> 16);
+        filter_rescale(f);
+        MTM_UNROLL
+        for (int k = 0; k < DM::DM; ++k) zt[k] = zn[k];
+        MTM_UNROLL
+        for (int k = 0; k < DM::LM; ++k) xt[k] = xn[k];
+    }
+    bad |= f.bad;
+    return filter_finish(f);
+}
+
+// finiteness masks of the unconditional stacked mean [m A^t | m A^t H] for one cluster; run by one
+// thread per cluster in a kernel prologue.  T0 words.
+template <class DM>
+__device__ void mean_finite_masks(const DM &dm, const double *prow, int T0, uint32_t *fin) {
+    const ParamView<DM> p(dm, prow);
+    const int d = dm.d(), l = dm.l();
+    double mu[MTM_MAX_DIM], nm[MTM_MAX_DIM];
+    for (int i = 0; i < d; ++i) mu[i] = p.m[i];
+    for (int t = 0; t < T0; ++t) {
+        if (t > 0) {
+            for (int j = 0; j < d; ++j) {
+                double s = 0.0;
+                for (int i = 0; i < d; ++i) s = fma(mu[i], p.A[i * d + j], s);
+                nm[j] = s;
+            }
+            for (int j = 0; j < d; ++j) mu[j] = nm[j];
+        }
+        uint32_t m = 0;
+        for (int j = 0; j < d; ++j) m |= finite_bits(mu[j]) ? (1u << j) : 0u;
+        for (int b = 0; b < l; ++b) {
+            double s = 0.0;
+            for (int i = 0; i < d; ++i) s = fma(mu[i], p.H[i * l + b], s);
+            m |= finite_bits(s) ? (1u << (16 + b)) : 0u;
+        }
+        fin[t] = m;
+    }
+}
+
+}  // namespace mtm

@@ -1,0 +1,54 @@
+// DFMA-saturating micro-kernel: the measured FP64 peak of this device, denominator of the FP64
+// roofline (MEASURED_PEAKS.json carries only HBM and bf16 numbers).
+#include "common.cuh"
+
+namespace mtm {
+
+constexpr int kChains = 8;
+
+__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b) {
+    double x[kChains];
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) x[k] = (double)(threadIdx.x + k) * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int k = 0; k < kChains; ++k) x[k] = fma(x[k], a, b);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) s += x[k];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true: keeps the chains alive
+}
+
+cudaError_t run_fp64_peak(int reps, int sm_count, cudaStream_t s, double *tflops) {
+    const int grid = sm_count * 8, threads = 256, iters = 4096;
+    double *out = nullptr;
+    cudaError_t e = cudaMalloc(&out, sizeof(double) * grid * threads);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    double best_ms = 1e30;
+    for (int r = 0; r < reps + 2; ++r) {  // two warm-up launches
+        cudaEventRecord(t0, s);
+        dfma_kernel<<<grid, threads, 0, s>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(t1, s);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (r >= 2 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(out);
+    if (e != cudaSuccess) return e;
+    const double flop = 2.0 * (double)grid * threads * kChains * 8.0 * iters;
+    *tflops = flop / (best_ms * 1e-3) * 1e-12;
+    return cudaGetLastError();
+}
+
+}  // namespace mtm

@@ -1,0 +1,192 @@
+"""Thin object layer over the C ABI: torch tensors carry the device buffers and the stream,
+nothing else.  One ``Engine`` per (process, device)."""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi as C
+
+
+class DeviceData:
+    """A data set resident in HBM: z (T, n, d) or None, x (T, n, l), float64, contiguous."""
+
+    def __init__(self, states, observations, device):
+        def up(a):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                t = a.to(device=device, dtype=torch.float64)
+            else:
+                a = np.ascontiguousarray(np.atleast_3d(np.asarray(a, dtype=np.float64)))
+                t = torch.from_numpy(a).to(device)
+            return t.contiguous()
+
+        self.z = up(states)
+        self.x = up(observations)
+        if self.x.dim() != 3 or (self.z is not None and self.z.dim() != 3):
+            raise ValueError("states / observations must be (T, n, d|l) arrays")
+        self.T, self.n, self.l = (int(v) for v in self.x.shape)
+        if self.z is not None:
+            if tuple(self.z.shape[:2]) != (self.T, self.n):
+                raise ValueError("states and observations disagree on (T, n)")
+            self.d = int(self.z.shape[2])
+        else:
+            self.d = None
+
+    def struct(self, d=None):
+        s = C.MtmData()
+        s.z_dev = self.z.data_ptr() if self.z is not None else None
+        s.x_dev = self.x.data_ptr()
+        s.n, s.T, s.l = self.n, self.T, self.l
+        s.d = self.d if self.d is not None else int(d)
+        return s
+
+    def nbytes(self):
+        return (self.z.numel() if self.z is not None else 0) * 8 + self.x.numel() * 8
+
+
+class Engine:
+    _cache: dict = {}
+
+    @classmethod
+    def get(cls, device=None) -> "Engine":
+        if not torch.cuda.is_available():
+            raise C.MtmError("no CUDA device: mtm_b200 runs on a B200 only and has no CPU path")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if dev.index not in cls._cache:
+            cls._cache[dev.index] = Engine(dev)
+        return cls._cache[dev.index]
+
+    def __init__(self, device):
+        self.lib = C.load()
+        self.device = device
+        self.h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            self.stream = torch.cuda.current_stream(device)
+            C.check(self.lib.mtm_create(device.index, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(self.h)))
+        self.world, self.rank = 1, 0
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _sync_stream(self):
+        s = torch.cuda.current_stream(self.device)
+        C.check(self.lib.mtm_set_stream(self.h, ctypes.c_void_p(s.cuda_stream)), self.h)
+
+    def _chk(self, rc):
+        C.check(rc, self.h)
+
+    def param_stride(self, d, l):
+        return int(self.lib.mtm_param_stride(d, l))
+
+    def stats_stride(self, d, l):
+        return int(self.lib.mtm_stats_stride(d, l))
+
+    def launch_count(self):
+        return int(self.lib.mtm_launch_count(self.h))
+
+    def dev(self, a, dtype):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device).to(dtype).contiguous()
+
+    # -- operations ----------------------------------------------------------------------------
+    def bind(self, data: DeviceData):
+        st = data.struct()
+        self._chk(self.lib.mtm_set_data(self.h, ctypes.byref(st)))
+
+    def estep(self, data: DeviceData, params, n_c, T0, assign=None, count_switches=False, want_ll=False,
+              want_probs=False, want_prenorm=False, d=None, want_info=True):
+        """One E-step launch.  Returns dict(assign, ll, probs, prenorm, n_switches, min_count, status)."""
+        self._sync_stream()
+        st = data.struct(d)
+        n = data.n
+        params = self.dev(params, torch.float64)
+        if assign is None:
+            assign = torch.empty(n, dtype=torch.int32, device=self.device)
+            count_switches = False
+        mk = lambda flag: torch.empty((n_c, n), dtype=torch.float64, device=self.device) if flag else None
+        ll, probs, prenorm = mk(want_ll), mk(want_probs), mk(want_prenorm)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        info = C.EStepInfo()
+        self._chk(self.lib.mtm_estep(self.h, ctypes.byref(st), ptr(params), n_c, int(T0), ptr(assign),
+                                     1 if count_switches else 0, ptr(ll), ptr(probs), ptr(prenorm),
+                                     ctypes.byref(info) if want_info else None))
+        return dict(assign=assign, ll=ll, probs=probs, prenorm=prenorm, n_switches=int(info.n_switches),
+                    min_count=int(info.min_count), status=int(info.status))
+
+    def score(self, data: DeviceData, params, n_c, d=None):
+        self._sync_stream()
+        st = data.struct(d)
+        params = self.dev(params, torch.float64)
+        out = (ctypes.c_double * 2)()
+        status = ctypes.c_int32(0)
+        self._chk(self.lib.mtm_score(self.h, ctypes.byref(st), ctypes.c_void_p(params.data_ptr()), n_c, out,
+                                     ctypes.byref(status)))
+        return float(out[0]), float(out[1]), int(status.value)
+
+    def mstats(self, data: DeviceData, assign, n_c):
+        self._sync_stream()
+        self.bind(data)
+        stats = torch.empty((n_c, self.stats_stride(data.d, data.l)), dtype=torch.float64, device=self.device)
+        self._chk(self.lib.mtm_mstats(self.h, ctypes.c_void_p(assign.data_ptr()), n_c, ctypes.c_void_p(stats.data_ptr())))
+        return stats
+
+    def finalize(self, stats, n_c, d, l, n_total, alpha):
+        self._sync_stream()
+        params = torch.empty((n_c, self.param_stride(d, l)), dtype=torch.float64, device=self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._chk(self.lib.mtm_finalize(self.h, ctypes.c_void_p(stats.data_ptr()), n_c, d, l, int(n_total), float(alpha),
+                                        ctypes.c_void_p(params.data_ptr()), ctypes.c_void_p(status.data_ptr())))
+        return params, status
+
+    def mstep(self, data: DeviceData, assign, n_c, alpha):
+        self._sync_stream()
+        self.bind(data)
+        params = torch.empty((n_c, self.param_stride(data.d, data.l)), dtype=torch.float64, device=self.device)
+        info = C.EStepInfo()
+        self._chk(self.lib.mtm_mstep(self.h, ctypes.c_void_p(assign.data_ptr()), n_c, float(alpha),
+                                     ctypes.c_void_p(params.data_ptr()), ctypes.byref(info)))
+        return params, int(info.min_count), int(info.status)
+
+    def em_fit(self, data: DeviceData, assign, n_c, alpha, n_steps, params=None):
+        """train(): assign (int32 device tensor) is updated in place.  Returns (params, info dict)."""
+        self._sync_stream()
+        self.bind(data)
+        if params is None:
+            params = torch.full((n_c, self.param_stride(data.d, data.l)), float("nan"), dtype=torch.float64,
+                                device=self.device)
+        info = C.FitInfo()
+        cap = max(1, int(n_steps))
+        hist = (ctypes.c_int64 * cap)()
+        self._chk(self.lib.mtm_em_fit(self.h, n_c, float(alpha), int(n_steps), ctypes.c_void_p(assign.data_ptr()),
+                                      ctypes.c_void_p(params.data_ptr()), ctypes.byref(info), hist, cap))
+        return params, dict(exit_code=int(info.exit_code), exit=C.EXIT_NAMES.get(int(info.exit_code), "?"),
+                            n_e_steps=int(info.n_e_steps), n_m_steps=int(info.n_m_steps), status=int(info.status),
+                            last_switches=int(info.last_switches), min_count=int(info.min_count),
+                            switches=[int(hist[k]) for k in range(min(cap, int(info.n_e_steps)))])
+
+    def fp64_peak(self, reps=10):
+        self._sync_stream()
+        out = ctypes.c_double(0.0)
+        self._chk(self.lib.mtm_fp64_peak(self.h, reps, ctypes.byref(out)))
+        return float(out.value)
+
+    # -- sharding ------------------------------------------------------------------------------
+    def unique_id(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        C.check(self.lib.mtm_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, id_bytes: bytes, world: int, rank: int):
+        buf = ctypes.create_string_buffer(id_bytes, 128)
+        self._chk(self.lib.mtm_comm_init(self.h, buf, world, rank))
+        self.world, self.rank = world, rank
+
+    def comm_destroy(self):
+        self._chk(self.lib.mtm_comm_destroy(self.h))
+        self.world, self.rank = 1, 0

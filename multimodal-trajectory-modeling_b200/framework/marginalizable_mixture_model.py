@@ -1,0 +1,535 @@
+"""Drop-in for the reference's ``framework/marginalizable_mixture_model.py`` (MMM): the
+hard-assignment EM of a mixture of linear-Gaussian state-space models, with every number
+computed by the sm_100a kernels behind ``include/mtm_b200.h``.
+
+Same class name, constructor, attributes, method names, argument meaning and error behaviour as
+the reference class (MMM:39) for the EM / predict path; reporting and plotting helpers of the
+reference (MMM:321-437, 1473-1916) are presentation code and are not part of this path.
+
+There is no CPU fallback: without the CUDA library / a B200 every numeric method raises.
+"""
+
+from __future__ import annotations
+
+import datetime
+import glob
+import gzip
+import hashlib
+import os
+import pickle
+import string
+
+import numpy as np
+import torch
+
+from .. import _capi as C
+from ..engine import DeviceData, Engine
+
+np_eps = np.finfo(float).eps
+# reference: <repo>/tmp (MMM:36, 229).  Configurable because a package directory may be read-only.
+home_dir = os.environ.get("MTM_B200_HOME", os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _raise_for_status(status: int, alpha: float = 0.0):
+    """Re-raise what the reference raises for the same numerical condition."""
+    if status & C.STATUS_NONFINITE:
+        # numba's det/solve on a covariance block holding NaN/inf (SSM:771-773)
+        raise np.linalg.LinAlgError("Array must not contain infs or NaNs.")
+    if status & C.STATUS_SINGULAR:
+        raise np.linalg.LinAlgError("Matrix is singular to machine precision.")
+    if status & C.STATUS_EMPTY_FIT:
+        if alpha > 2 * np_eps:  # sklearn Ridge.fit on 0 samples (MMM:1226-1227)
+            raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by Ridge.")
+        raise np.linalg.LinAlgError("Arrays cannot be empty")  # numba lstsq (MMM:1194)
+    if status & C.STATUS_CHOL_FAIL:
+        raise np.linalg.LinAlgError("rank-deficient regression design: normal equations not positive definite")
+
+
+class MMLinGaussSS_marginalizable:
+    """Probabilistic mixture of linear-Gaussian state-space models trained by hard-assignment EM
+    (reference: MMM:39-1471)."""
+
+    def __init__(
+        self,
+        n_clusters: int,
+        states: np.array,
+        observations: np.array,
+        random_seed: int = 42,
+        init: str = "random",
+        alpha: float = 0.0,
+        *,
+        device=None,
+        _shared_data: DeviceData = None,
+    ):
+        """Same arguments as the reference constructor (MMM:45-53); ``device`` (keyword-only,
+        optional) picks the CUDA device."""
+        states, observations = map(np.atleast_3d, (states, observations))
+        self.n_clusters = int(n_clusters)
+        self.states = np.array(states)
+        self.observations = np.array(observations)
+        self.n_timesteps, self.n_data, self.d_states = self.states.shape
+        self.d_observations = self.observations.shape[-1]
+        d, l, k = self.d_states, self.d_observations, self.n_clusters
+
+        # Placeholder parameters from the unseeded global RNG, as the reference draws them
+        # (MMM:83-125); `train` overwrites them in its first M-step.
+        self.cluster_propensities = np.ones(shape=[k]) / k
+        self.init_state_means = [np.random.normal(size=[d]) for _ in range(k)]
+        spd = lambda m: m @ m.T + np.eye(m.shape[0])
+        self.init_state_covs = [spd(np.random.normal(size=[d, d])) for _ in range(k)]
+        self.transition_matrices = [np.random.normal(size=[d, d]) for _ in range(k)]
+        self.transition_covs = [spd(np.random.normal(size=[d, d])) for _ in range(k)]
+        self.measurement_matrices = [np.random.normal(size=[d, l]) for _ in range(k)]
+        self.measurement_covs = [spd(np.random.normal(size=[l, l])) for _ in range(k)]
+
+        self.random_seed = random_seed
+        self.rng = np.random.default_rng(seed=self.random_seed)
+        self.init = init
+        self.alpha = alpha if alpha > 2 * np_eps else 0
+        self.cluster_assignment = self._initial_assignment()
+
+        self._correspondence = dict(zip(range(k), string.ascii_uppercase))
+        self.inverse_correspondence = {v: c for c, v in self._correspondence.items()}
+        self.hex_hash = hashlib.md5(
+            self.states.tobytes()
+            + self.observations.tobytes()
+            + str(self.n_clusters).encode("utf-8")
+            + (np.format_float_positional(self.alpha, unique=True).encode("utf-8")
+               if self.alpha > 2 * np_eps else b"")
+        ).hexdigest()  # MMM:177-188
+        self.time_stamp = (datetime.datetime.now(datetime.timezone.utc).replace(microsecond=0)
+                           .astimezone().isoformat())
+        self.last_trained = None
+
+        self._device = device
+        self._data = _shared_data  # uploaded lazily
+        self.fit_info = None       # dict from the last train(): exit, n_e_steps, switches, ...
+
+    # ------------------------------------------------------------------ initial assignment
+    def _initial_assignment(self):
+        """Host-side, exactly the reference's three initialisers (MMM:131-168)."""
+        import sklearn.cluster as skl_cluster
+
+        match self.init:
+            case "k-means" | "kmeans":
+                idx = np.argmax(np.isfinite(self.states).all(axis=2), axis=0).ravel()
+                first = self.states[idx, np.arange(self.n_data), :]
+                with np.errstate(all="ignore"):
+                    first = np.where(np.isfinite(first), first, np.nanmean(first, axis=0, keepdims=True))
+                return skl_cluster.KMeans(n_clusters=self.n_clusters, init="k-means++",
+                                          random_state=self.random_seed).fit_predict(first)
+            case "kmeans-all" | "k-means-all":
+                flat = np.transpose(self.states, (1, 0, 2)).reshape(self.n_data, -1)
+                return skl_cluster.KMeans(n_clusters=self.n_clusters, init="k-means++",
+                                          random_state=self.random_seed).fit_predict(flat)
+            case _:
+                return self.rng.integers(low=0, high=self.n_clusters, size=self.n_data)
+
+    # ------------------------------------------------------------------ small properties
+    @property
+    def n_free_params(self) -> int:
+        """MMM:197-214."""
+        tri = lambda m: len(np.triu_indices_from(np.atleast_2d(m))[0])
+        return (sum(np.size(x) for x in [self.cluster_propensities] + list(self.init_state_means)
+                    + list(self.transition_matrices) + list(self.measurement_matrices))
+                + sum(tri(x) for x in list(self.init_state_covs) + list(self.transition_covs)
+                      + list(self.measurement_covs)))
+
+    @property
+    def correspondence(self) -> dict:
+        return self._correspondence
+
+    @correspondence.setter
+    def correspondence(self, corr: dict) -> None:
+        self._correspondence = corr
+        self.inverse_correspondence = {v: k for k, v in self._correspondence.items()}
+
+    # ------------------------------------------------------------------ device plumbing
+    @property
+    def engine(self) -> Engine:
+        return Engine.get(self._device)
+
+    def _train_data(self) -> DeviceData:
+        if self._data is None:
+            self._data = DeviceData(self.states, self.observations, self.engine.device)
+        return self._data
+
+    def _packed_params(self) -> np.ndarray:
+        """(n_c, 1+d+3d^2+dl+l^2) rows [pi | m | S | A | Gamma | H | Lambda] (C-ABI layout)."""
+        d, l = self.d_states, self.d_observations
+        rows = []
+        for c in range(self.n_clusters):
+            rows.append(np.concatenate([
+                [self.cluster_propensities[c]],
+                np.reshape(self.init_state_means[c], d),
+                np.reshape(self.init_state_covs[c], d * d),
+                np.reshape(self.transition_matrices[c], d * d),
+                np.reshape(self.transition_covs[c], d * d),
+                np.reshape(self.measurement_matrices[c], d * l),
+                np.reshape(self.measurement_covs[c], l * l)]))
+        return np.ascontiguousarray(np.stack(rows), dtype=np.float64)
+
+    def _unpack_params(self, packed) -> None:
+        P = packed.detach().cpu().numpy() if isinstance(packed, torch.Tensor) else np.asarray(packed)
+        d, l = self.d_states, self.d_observations
+        o = [0]
+
+        def take(shape):
+            size = int(np.prod(shape))
+            out = [P[c, o[0]:o[0] + size].reshape(shape).copy() for c in range(self.n_clusters)]
+            o[0] += size
+            return out
+
+        self.cluster_propensities = P[:, 0].copy()
+        o[0] = 1
+        self.init_state_means = take((d,))
+        self.init_state_covs = take((d, d))
+        self.transition_matrices = take((d, d))
+        self.transition_covs = take((d, d))
+        self.measurement_matrices = take((d, l))
+        self.measurement_covs = take((l, l))
+
+    def _assign_dev(self):
+        return torch.from_numpy(np.ascontiguousarray(self.cluster_assignment, dtype=np.int32)).to(self.engine.device)
+
+    def _resolve(self, states, observations):
+        """The reference's data-override rule: if `states` is None BOTH come from the training
+        set (MMM:469-471, 756-758); otherwise the given arrays are used."""
+        if states is None:
+            return self._train_data()
+        if observations is None:
+            raise TypeError("observations must be given together with states")
+        return DeviceData(states, observations, self.engine.device)
+
+    # ------------------------------------------------------------------ likelihoods
+    def _estep(self, data, T0, *, ll=False, probs=False, prenorm=False, d=None):
+        res = self.engine.estep(data, self._packed_params(), self.n_clusters, T0, want_ll=ll, want_probs=probs,
+                                want_prenorm=prenorm, d=d)
+        _raise_for_status(res["status"], self.alpha)
+        return res
+
+    def conditional_log_likelihoods_first_T0_steps(self, c: int, T0: int, *, states=None, observations=None):
+        """log p(z_i, x_i | cluster c) on steps 1..T0 (MMM:439-494)."""
+        assert 1 <= T0 <= self.n_timesteps
+        data = self._resolve(states, observations)
+        return self._estep(data, T0, ll=True)["ll"][c].cpu().numpy()
+
+    def conditional_log_likelihoods(self, c: int, *, states=None, observations=None):
+        """MMM:496-530."""
+        return self.conditional_log_likelihoods_first_T0_steps(c, self.n_timesteps, states=states,
+                                                               observations=observations)
+
+    def log_likelihood_matrix(self, *, states=None, observations=None, T0=None) -> np.ndarray:
+        """(n_clusters, n) matrix of conditional log-likelihoods in ONE launch (the reference needs
+        n_clusters calls of `conditional_log_likelihoods`)."""
+        data = self._resolve(states, observations)
+        return self._estep(data, self.n_timesteps if T0 is None else T0, ll=True)["ll"].cpu().numpy()
+
+    def mle_cluster_assignment(self, *, return_probs: bool = False, return_prenormalized_log_probs: bool = False,
+                               states=None, observations=None):
+        """argmax_c pi_c exp(ll_c) [, probs (n_c, n)] [, log pi_c + ll_c (n_c, n)]  (MMM:724-791)."""
+        data = self._resolve(states, observations)
+        want_p = return_probs or return_prenormalized_log_probs
+        res = self._estep(data, self.n_timesteps, probs=want_p, prenorm=return_prenormalized_log_probs)
+        assignments = res["assign"].cpu().numpy().astype(np.int64)
+        if not want_p:
+            return assignments
+        probs = res["probs"].cpu().numpy()
+        if not return_prenormalized_log_probs:
+            return assignments, probs
+        return assignments, probs, res["prenorm"].cpu().numpy()
+
+    def cluster_assignment_index(self, *, cluster: str = "A", states=None, observations=None):
+        """Pre-normalised log-odds of assignment to `cluster` (MMM:793-806)."""
+        return self.mle_cluster_assignment(states=states, observations=observations, return_probs=True,
+                                           return_prenormalized_log_probs=True)[-1][self.inverse_correspondence[cluster]]
+
+    def cluster_propensities_over_time(self, *, states=None, observations=None):
+        """(T, n, n_c) membership probabilities from the first t+1 steps (MMM:532-577)."""
+        data = self._resolve(states, observations)
+        out = []
+        for t in range(min(self.n_timesteps, data.T)):
+            L = self._estep(data, t + 1, ll=True)["ll"].cpu().numpy()
+            out.append((self.cluster_propensities[:, None] * np.exp(L)).T)
+        pc_t = np.stack(out, axis=0)
+        pc_t /= np.sum(pc_t, axis=-1, keepdims=True)
+        assert np.all(pc_t >= 0.0) and np.allclose(np.sum(pc_t, axis=-1), 1.0)
+        return pc_t
+
+    def initial_full_data_cluster_assignment(self, *, states=None, observations=None):
+        """Assignment from the first time step only (MMM:909-941)."""
+        data = self._resolve(states, observations)
+        return self._estep(data, 1)["assign"].cpu().numpy().astype(np.int64)
+
+    # ---- observation-only route (hidden states marginalised) ------------------------------
+    def _obs_data(self, observations):
+        if observations is None:
+            tr = self._train_data()
+            od = DeviceData.__new__(DeviceData)
+            od.z, od.x, od.T, od.n, od.l, od.d = None, tr.x, tr.T, tr.n, tr.l, None
+            return od
+        return DeviceData(None, observations, self.engine.device)
+
+    def observed_condl_log_lik_first_T0_steps(self, c: int, T0: int, *, observations=None):
+        """log p(x_i | cluster c) on steps 1..T0 (MMM:997-1048)."""
+        assert 1 <= T0 <= self.n_timesteps
+        return self._estep(self._obs_data(observations), T0, ll=True, d=self.d_states)["ll"][c].cpu().numpy()
+
+    def observed_conditional_log_likelihoods(self, c: int, observations=None):
+        """MMM:1050-1075."""
+        return self.observed_condl_log_lik_first_T0_steps(c, self.n_timesteps, observations=observations)
+
+    def observed_cluster_propensities_over_time(self, observations=None):
+        """MMM:1077-1123."""
+        data = self._obs_data(observations)
+        out = []
+        for t in range(data.T):
+            L = self._estep(data, t + 1, ll=True, d=self.d_states)["ll"].cpu().numpy()
+            out.append((self.cluster_propensities[:, None] * np.exp(L)).T)
+        pc_t = np.stack(out, axis=0)
+        pc_t /= np.sum(pc_t, axis=-1, keepdims=True)
+        assert np.all(pc_t >= 0.0) and np.allclose(np.sum(pc_t, axis=-1), 1.0)
+        return pc_t
+
+    def observations_mle_cluster_assignment(self, *, return_probs: bool = False, observations=None):
+        """argmax over p(x | c) pi_c  [, probs]  (MMM:1125-1165)."""
+        res = self._estep(self._obs_data(observations), self.n_timesteps, probs=return_probs, d=self.d_states)
+        a = res["assign"].cpu().numpy().astype(np.int64)
+        return (a, res["probs"].cpu().numpy()) if return_probs else a
+
+    # ---- scores --------------------------------------------------------------------------------
+    def _score(self, states, observations):
+        data = self._resolve(states, observations)
+        q, ll, status = self.engine.score(data, self._packed_params(), self.n_clusters)
+        _raise_for_status(status, self.alpha)
+        return q, ll
+
+    def e_complete_data_log_lik(self, *, states=None, observations=None) -> float:
+        """Q = sum_i log pi_{a_i} + ll[a_i, i]  (MMM:579-624)."""
+        return self._score(states, observations)[0]
+
+    def model_log_likelihood(self, *, states=None, observations=None):
+        """sum_i log sum_c pi_c exp(ll_ci)  (MMM:626-666)."""
+        return self._score(states, observations)[1]
+
+    def aic(self, states=None, observations=None) -> float:
+        """MMM:668-693."""
+        return -2 * self.model_log_likelihood(states=states, observations=observations) + 2 * self.n_free_params
+
+    def bic(self, states=None, observations=None) -> float:
+        """MMM:695-722."""
+        n = self.n_data if states is None else np.atleast_3d(states).shape[1]
+        return (-2 * self.model_log_likelihood(states=states, observations=observations)
+                + np.log(n) * self.n_free_params)
+
+    # ---- predictions built on the assignment probabilities (host arithmetic, O(n d)) ----------
+    def one_step_ahead_predictions(self, *, states, observations):
+        """MMM:808-850."""
+        probs = self.mle_cluster_assignment(states=states, observations=observations, return_probs=True)[1]
+        return self._mix_next(probs, np.atleast_3d(states), np.atleast_3d(observations))
+
+    def one_step_ahead_predictions_no_history(self, *, states, observations):
+        """MMM:852-907."""
+        states, observations = np.atleast_3d(states), np.atleast_3d(observations)
+        s0 = np.nan * np.ones_like(states)
+        s0[-1] = states[-1]
+        o0 = np.nan * np.ones_like(observations)
+        o0[-1] = observations[-1]
+        probs = self.mle_cluster_assignment(states=s0, observations=o0, return_probs=True)[1]
+        return self._mix_next(probs, states, observations)
+
+    def _mix_next(self, probs, states, observations):
+        nxt_s = np.zeros(shape=(1, *states.shape[1:]))
+        nxt_o = np.zeros(shape=(1, *observations.shape[1:]))
+        last = states[-1]
+        assert probs.shape == (self.n_clusters, last.shape[0])
+        for c in range(self.n_clusters):
+            s_c = last @ self.transition_matrices[c]
+            o_c = s_c @ self.measurement_matrices[c]
+            nxt_s += np.expand_dims(probs[c], axis=-1) * s_c
+            nxt_o += np.expand_dims(probs[c], axis=-1) * o_c
+        return nxt_s, nxt_o
+
+    def predictions_from_initial_data(self, *, states=None, observations=None):
+        """MMM:943-995 (predicts from the TRAINING set's first states, like the reference)."""
+        a = self.initial_full_data_cluster_assignment(states=states, observations=observations)
+        ps = np.zeros_like(self.states if states is None else states)
+        po = np.zeros_like(self.observations if observations is None else observations)
+        for i in range(self.n_data):
+            z = np.atleast_1d(self.states[0, i, :])
+            A = np.atleast_2d(self.transition_matrices[a[i]])
+            H = np.atleast_2d(self.measurement_matrices[a[i]])
+            for t in range(ps.shape[0]):
+                ps[t, i, :] = z
+                if t < po.shape[0]:
+                    po[t, i, :] = z @ H
+                z = z @ A
+            for t in range(ps.shape[0], po.shape[0]):
+                po[t, i, :] = z @ H
+                z = z @ A
+        return ps, po
+
+    # ------------------------------------------------------------------ EM
+    @staticmethod
+    def regress(input_exogenous, output_endogenous):
+        """Least-squares coefficients and residual covariance (MMM:1167-1200) from the moment
+        kernel: one pseudo-cluster holding every row."""
+        return MMLinGaussSS_marginalizable.regress_alpha(input_exogenous, output_endogenous, 0.0)
+
+    @staticmethod
+    def regress_alpha(input_exogenous, output_endogenous, alpha: float):
+        """Ridge coefficients and residual covariance (MMM:1202-1233) on the device: the rows are
+        presented to the M-step kernels as (z_t, x_t) pairs of a single cluster."""
+        X = np.atleast_2d(np.asarray(input_exogenous, dtype=np.float64))
+        Y = np.atleast_2d(np.asarray(output_endogenous, dtype=np.float64))
+        eng = Engine.get()
+        data = DeviceData(X[None], Y[None], eng.device)
+        assign = torch.zeros(X.shape[0], dtype=torch.int32, device=eng.device)
+        params, _, status = eng.mstep(data, assign, 1, alpha if alpha > 2 * np_eps else 0.0)
+        _raise_for_status(status & ~C.STATUS_EMPTY_FIT if X.shape[0] else status, alpha)
+        p = params.cpu().numpy()[0]
+        d, l = X.shape[1], Y.shape[1]
+        o = 1 + d + 3 * d * d
+        return p[o:o + d * l].reshape(d, l).copy(), p[o + d * l:o + d * l + l * l].reshape(l, l).copy()
+
+    def E_step(self) -> int:
+        """New hard assignment; returns the number of switches (MMM:1235-1252)."""
+        eng = self.engine
+        assign = self._assign_dev()
+        res = eng.estep(self._train_data(), self._packed_params(), self.n_clusters, self.n_timesteps, assign=assign,
+                        count_switches=True)
+        _raise_for_status(res["status"], self.alpha)
+        self.cluster_assignment = assign.cpu().numpy().astype(np.int64)
+        return int(res["n_switches"])
+
+    def M_step(self) -> None:
+        """Parameters from the current hard assignment (MMM:1254-1308)."""
+        params, _, status = self.engine.mstep(self._train_data(), self._assign_dev(), self.n_clusters, self.alpha)
+        self._unpack_params(params)
+        _raise_for_status(status, self.alpha)
+
+    def train(self, *, verbose: bool = False, n_steps: int = 1000):
+        """EM until no assignment changes, a cluster gets near-empty, or n_steps (MMM:1310-1366).
+        The loop is resident on the device; only the control block comes back."""
+        eng = self.engine
+        assign = self._assign_dev()
+        params, info = eng.em_fit(self._train_data(), assign, self.n_clusters, self.alpha, n_steps)
+        self.fit_info = info
+        self.cluster_assignment = assign.cpu().numpy().astype(np.int64)
+        if info["exit"] == "guard0":
+            if verbose:
+                print("Encountered near-empty cluster.")
+            return self  # like the reference: returns before any M-step, last_trained stays None
+        self._unpack_params(params)
+        if info["exit"] == "error" or info["status"]:
+            _raise_for_status(info["status"], self.alpha)
+        if verbose:
+            if info["exit"] == "converged":
+                print(f"Optimisation completed in {info['n_e_steps'] - 1} steps.")
+            elif info["exit"] == "guard":
+                print("Encountered near-empty cluster.")
+        self.last_trained = (datetime.datetime.now(datetime.timezone.utc).replace(microsecond=0)
+                             .astimezone().isoformat())
+        return self
+
+    def train_with_multiple_random_starts(self, *, n_starts: int = 10, verbose: bool = False, n_steps: int = 100,
+                                          return_objectives: bool = False, use_cache: bool = True):
+        """k-means start (seed 0) + n_starts random starts (seeds 100+i); best by strict > on Q
+        (MMM:1368-1471).  The training set is uploaded once and shared by all restarts."""
+        if bool(use_cache):
+            try:
+                pfile = sorted(glob.glob(os.path.join(home_dir, "tmp", f"mmm-{self.hex_hash}*")),
+                               key=os.path.getmtime).pop()
+                best_mdl = MMLinGaussSS_marginalizable.from_pickle(
+                    pfile, training_data={"states": self.states, "observations": self.observations})
+                assert self.hex_hash == best_mdl.hex_hash
+                if verbose:
+                    print(f"Loaded model {best_mdl.last_trained=} from cache.")
+                return best_mdl
+            except IndexError:
+                if verbose:
+                    print("No model found in cache.")
+            except Exception as err:  # noqa: BLE001 - mirrors the reference
+                if verbose:
+                    print(f"Issue loading cached model -- encountered {err}")
+
+        shared = self._train_data()
+        best_mdl = MMLinGaussSS_marginalizable(n_clusters=self.n_clusters, states=self.states,
+                                               observations=self.observations, random_seed=0, init="kmeans",
+                                               alpha=self.alpha, device=self._device, _shared_data=shared)
+        try:
+            best_mdl = best_mdl.train(verbose=verbose, n_steps=n_steps)
+        except Exception:  # noqa: BLE001 - the reference swallows every failure of a start
+            pass
+        if return_objectives:
+            objective_list = [best_mdl.e_complete_data_log_lik()]
+        for i in range(n_starts):
+            try:
+                mix_mdl = MMLinGaussSS_marginalizable(n_clusters=self.n_clusters, states=self.states,
+                                                      observations=self.observations, random_seed=100 + i,
+                                                      alpha=self.alpha, device=self._device,
+                                                      _shared_data=shared).train(verbose=verbose, n_steps=n_steps)
+                if return_objectives:
+                    objective_list.append(mix_mdl.e_complete_data_log_lik())
+                if mix_mdl.e_complete_data_log_lik() > best_mdl.e_complete_data_log_lik():
+                    best_mdl = mix_mdl
+            except Exception:  # noqa: BLE001,S110
+                pass
+        if not np.isfinite(best_mdl.e_complete_data_log_lik()):
+            raise Exception("training failed")
+        if use_cache:
+            best_mdl.to_pickle()
+        if return_objectives:
+            return best_mdl, np.array(objective_list)
+        return best_mdl
+
+    # ------------------------------------------------------------------ persistence (MMM:227-319)
+    def to_pickle(self, save_location=None, there_can_only_be_one: bool = True, include_training_data: bool = False):
+        save_location = os.path.join(home_dir, "tmp") if save_location is None else save_location
+        os.makedirs(save_location, exist_ok=True)
+        ts = datetime.datetime.now(datetime.timezone.utc).strftime("%Y%m%dT%H%MZ")
+        if there_can_only_be_one:
+            for f in glob.glob(os.path.join(save_location, f"mmm-{self.hex_hash}*")):
+                os.remove(f)
+        payload = {
+            "n_clusters": self.n_clusters,
+            "cluster_propensities": self.cluster_propensities,
+            "init_state_means": self.init_state_means,
+            "init_state_covs": self.init_state_covs,
+            "transition_matrices": self.transition_matrices,
+            "transition_covs": self.transition_covs,
+            "measurement_matrices": self.measurement_matrices,
+            "measurement_covs": self.measurement_covs,
+            "random_seed": self.random_seed,
+            "rng": self.rng,
+            "init": self.init,
+            "alpha": self.alpha,
+            "cluster_assignment": self.cluster_assignment,
+            "correspondence": self.correspondence,
+            "inverse_correspondence": self.inverse_correspondence,
+            "hex_hash": self.hex_hash,
+            "time_stamp": self.time_stamp,
+            "last_trained": self.last_trained,
+        }
+        if include_training_data:
+            payload |= {"states": self.states, "observations": self.observations}
+        with gzip.open(os.path.join(save_location, f"mmm-{self.hex_hash}-{ts}.p.gz"), "wb") as f:
+            pickle.dump(payload, f)
+
+    @staticmethod
+    def from_pickle(file, training_data: dict = None):
+        opener = gzip.open if os.path.splitext(file)[-1] == ".gz" else open
+        with opener(file, "rb") as f:
+            md = pickle.load(f)
+        src = training_data if training_data is not None else md
+        mdl = MMLinGaussSS_marginalizable(n_clusters=md["n_clusters"], states=src["states"],
+                                          observations=src["observations"], random_seed=md["random_seed"],
+                                          init=md["init"], alpha=md["alpha"] if "alpha" in md else 0)
+        for key in ("cluster_propensities", "init_state_means", "init_state_covs", "transition_matrices",
+                    "transition_covs", "measurement_matrices", "measurement_covs", "rng", "cluster_assignment"):
+            setattr(mdl, key, md[key])
+        mdl.correspondence = md["correspondence"]
+        mdl.inverse_correspondence = md["inverse_correspondence"]
+        mdl.time_stamp = md["time_stamp"]
+        mdl.last_trained = md["last_trained"]
+        return mdl

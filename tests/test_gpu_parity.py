@@ -1,0 +1,386 @@
+"""Parity of the CUDA path (through the drop-in class and the C ABI) with the reference:
+golden vectors produced by the unmodified reference (tests/golden) and the CPU oracle.
+
+Bar (BASELINE.json north_star): cluster assignments, switch counts and iteration counts
+bit-exact; log-likelihoods, parameters, probabilities and scores within 1e-9 relative."""
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def relerr(a, b):
+    a, b = np.atleast_1d(np.asarray(a, dtype=float)), np.atleast_1d(np.asarray(b, dtype=float))
+    assert a.shape == b.shape, (a.shape, b.shape)
+    both_nan = np.isnan(a) & np.isnan(b)
+    d = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    d[both_nan] = 0.0
+    return float(np.max(d)) if d.size else 0.0
+
+
+@pytest.fixture(scope="module")
+def mix():
+    import mtm_b200  # noqa: F401
+    from mtm_b200.framework import marginalizable_mixture_model as mixmodel
+
+    return mixmodel
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import mtm_b200
+
+    return mtm_b200.Engine.get()
+
+
+def _case(g_em, key):
+    n, T, d, l, n_c, seed, n_steps = (int(v) for v in g_em[f"{key}_meta"])
+    return dict(z=g_em[f"{key}_z"], x=g_em[f"{key}_x"], n=n, T=T, d=d, l=l, n_c=n_c, seed=seed,
+                n_steps=n_steps, alpha=float(g_em[f"{key}_alpha"]))
+
+
+def _set_params(mdl, packed):
+    mdl._unpack_params(np.asarray(packed))
+
+
+def _packed_single(g, k):
+    return np.concatenate([[1.0], g(f"s{k}_m").ravel(), g(f"s{k}_S").ravel(), g(f"s{k}_A").ravel(),
+                           g(f"s{k}_G").ravel(), g(f"s{k}_H").ravel(), g(f"s{k}_L").ravel()])[None]
+
+
+def test_loglik_golden(g_ssm, eng):
+    """SSM-level vectors: every (T, d, l) shape incl. the generic-dimension kernel, NaN / +-inf /
+    all-missing / suffix-missing rows, joint and observation-only."""
+    import mtm_b200
+
+    for k, (T, d, l) in enumerate(g_ssm["shapes"]):
+        g = lambda name: g_ssm[name]
+        P = _packed_single(g, k)
+        data = mtm_b200.DeviceData(g(f"s{k}_z"), g(f"s{k}_x"), eng.device)
+        res = eng.estep(data, P, 1, T, want_ll=True)
+        assert res["status"] == 0
+        ll = res["ll"].cpu().numpy()[0]
+        assert relerr(ll, g(f"s{k}_ll")) < RTOL, (T, d, l)
+        assert ll[1] == 0.0  # all-missing row -> (-)0.0 like the reference
+        xo = mtm_b200.DeviceData(None, g(f"s{k}_x"), eng.device)
+        llx = eng.estep(xo, P, 1, T, want_ll=True, d=int(d))["ll"].cpu().numpy()[0]
+        assert relerr(llx, g(f"s{k}_llx")) < RTOL, (T, d, l)
+
+
+@pytest.mark.parametrize("key", ["c2s", "c3s", "slow", "adnish", "mmmtest", "oned", "short", "guardexit"])
+def test_em_trace(g_em, mix, key):
+    c = _case(g_em, key)
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=c["n_c"], states=c["z"], observations=c["x"],
+                                          random_seed=c["seed"], alpha=c["alpha"])
+    assert np.array_equal(mdl.cluster_assignment, g_em[f"{key}_assign0"])
+    mdl.train(n_steps=c["n_steps"])
+    info = mdl.fit_info
+    assert info["switches"] == list(g_em[f"{key}_switches"]), info
+    assert info["n_e_steps"] == len(g_em[f"{key}_switches"])
+    assert np.array_equal(mdl.cluster_assignment, g_em[f"{key}_assign"])
+    assert mdl.cluster_assignment.dtype == np.int64
+    assert relerr(mdl._packed_params(), g_em[f"{key}_params"]) < RTOL
+    expect_exit = {"short": "exhausted", "guardexit": "guard"}.get(key, "converged")
+    assert info["exit"] == expect_exit
+    if key == "guardexit":
+        return
+    # outputs of the trained model
+    a, probs, prenorm = mdl.mle_cluster_assignment(return_probs=True, return_prenormalized_log_probs=True)
+    assert np.array_equal(a, g_em[f"{key}_mle_assign"])
+    assert relerr(probs, g_em[f"{key}_probs"]) < RTOL
+    assert relerr(prenorm, g_em[f"{key}_prenorm"]) < RTOL
+    assert relerr(mdl.log_likelihood_matrix(), g_em[f"{key}_ll"]) < RTOL
+    assert relerr(mdl.conditional_log_likelihoods(0), g_em[f"{key}_ll"][0]) < RTOL
+    assert relerr(mdl.e_complete_data_log_lik(), g_em[f"{key}_Q"]) < RTOL
+    assert relerr(mdl.model_log_likelihood(), g_em[f"{key}_LL"]) < RTOL
+    assert relerr(mdl.aic(), g_em[f"{key}_aic"]) < RTOL
+    assert relerr(mdl.bic(), g_em[f"{key}_bic"]) < RTOL
+    assert mdl.n_free_params == int(g_em[f"{key}_nfree"])
+    T = c["T"]
+    for t0 in range(1, T + 1):
+        got = mdl.log_likelihood_matrix(states=c["z"][:, :150], observations=c["x"][:, :150], T0=t0)
+        assert relerr(got, g_em[f"{key}_ll_T0"][t0 - 1]) < RTOL
+    # held-out style calls: fewer time steps than training, then hidden states all missing
+    zt, xt = c["z"][: max(1, T - 1), : c["n"] // 3], c["x"][: max(1, T - 1), : c["n"] // 3]
+    a, pr, pn = mdl.mle_cluster_assignment(states=zt, observations=xt, return_probs=True,
+                                           return_prenormalized_log_probs=True)
+    assert np.array_equal(a, g_em[f"{key}_ho_assign"])
+    assert relerr(pr, g_em[f"{key}_ho_probs"]) < RTOL
+    assert relerr(pn, g_em[f"{key}_ho_prenorm"]) < RTOL
+    a2, pr2 = mdl.mle_cluster_assignment(states=np.nan * np.ones_like(zt), observations=xt, return_probs=True)
+    assert np.array_equal(a2, g_em[f"{key}_ho_nohid_assign"])
+    assert relerr(pr2, g_em[f"{key}_ho_nohid_probs"]) < RTOL
+    if f"{key}_obs_ll" in g_em.files:  # the reference's observation-only route (not for 1-d)
+        ao, po = mdl.observations_mle_cluster_assignment(return_probs=True)
+        assert np.array_equal(ao, g_em[f"{key}_obs_assign"])
+        assert relerr(po, g_em[f"{key}_obs_probs"]) < RTOL
+        for cidx in range(c["n_c"]):
+            assert relerr(mdl.observed_conditional_log_likelihoods(cidx), g_em[f"{key}_obs_ll"][cidx]) < RTOL
+        for t0 in (1, T // 2 + 1, T):
+            got = mdl.observed_condl_log_lik_first_T0_steps(1, t0, observations=c["x"][:, :150])
+            assert relerr(got, g_em[f"{key}_obs_ll_T0"][t0 - 1][1]) < RTOL
+
+
+@pytest.mark.parametrize("key", ["c2s", "adnish"])
+def test_single_steps(g_em, mix, key):
+    """E_step() / M_step() called one at a time reproduce every iterate of the reference."""
+    c = _case(g_em, key)
+    hist = g_em[f"{key}_assign_hist"].astype(np.int64)
+    ph = g_em[f"{key}_params_hist"]
+    sw = g_em[f"{key}_switches"]
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=c["n_c"], states=c["z"], observations=c["x"],
+                                          random_seed=c["seed"], alpha=c["alpha"])
+    mdl.M_step()
+    assert relerr(mdl._packed_params(), ph[0]) < RTOL
+    for it in range(len(sw)):
+        assert mdl.E_step() == int(sw[it])
+        assert np.array_equal(mdl.cluster_assignment, hist[it])
+        if it + 1 < len(ph):
+            mdl.M_step()
+            assert relerr(mdl._packed_params(), ph[it + 1]) < RTOL
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_multi_restart(g_restarts, mix, tag):
+    """train_with_multiple_random_starts: objectives of every start, the winner (strict >, k-means
+    incumbent) and — data set A — the NaN-mean-cluster quirk that makes the degenerate k-means
+    start win in the reference."""
+    z, x = g_restarts[f"{tag}_z"], g_restarts[f"{tag}_x"]
+    n, T, d, l, n_c, n_starts = (int(v) for v in g_restarts[f"{tag}_meta"])
+    proto = mix.MMLinGaussSS_marginalizable(n_clusters=n_c, states=z, observations=x)
+    km = mix.MMLinGaussSS_marginalizable(n_clusters=n_c, states=z, observations=x, random_seed=0, init="kmeans")
+    assert np.array_equal(km.cluster_assignment, g_restarts[f"{tag}_kmeans_assign0"])
+    best, obj = proto.train_with_multiple_random_starts(n_starts=n_starts, n_steps=100, use_cache=False,
+                                                        return_objectives=True)
+    assert relerr(obj, g_restarts[f"{tag}_objectives"]) < RTOL
+    assert best.random_seed == int(g_restarts[f"{tag}_best_seed"])
+    assert np.array_equal(best.cluster_assignment, g_restarts[f"{tag}_best_assign"])
+    assert relerr(best._packed_params(), g_restarts[f"{tag}_best_params"]) < RTOL
+    assert relerr(best.e_complete_data_log_lik(), g_restarts[f"{tag}_best_Q"]) < RTOL
+    assert relerr(best.model_log_likelihood(), g_restarts[f"{tag}_best_LL"]) < RTOL
+    assert relerr(best.aic(), g_restarts[f"{tag}_best_aic"]) < RTOL
+    assert relerr(best.bic(), g_restarts[f"{tag}_best_bic"]) < RTOL
+
+
+def test_adni_fold(g_adni, mix):
+    """config 1: ADNI fold 0 of inference-adni-xval.py (alpha = 1, k-means + 8 random starts) and
+    its held-out maskings (XVAL:146-247)."""
+    ztr, xtr, zte, xte = g_adni["ztr"], g_adni["xtr"], g_adni["zte"], g_adni["xte"]
+    alpha = float(g_adni["alpha"])
+    proto = mix.MMLinGaussSS_marginalizable(n_clusters=4, states=ztr, observations=xtr, init="k-means", alpha=alpha)
+    assert proto.hex_hash == str(g_adni["hex_hash"])
+    km = mix.MMLinGaussSS_marginalizable(n_clusters=4, states=ztr, observations=xtr, random_seed=0, init="kmeans",
+                                         alpha=alpha)
+    assert np.array_equal(km.cluster_assignment, g_adni["km_assign0"])
+    km.train(n_steps=100)
+    assert km.fit_info["switches"] == list(g_adni["km_switches"])
+    assert np.array_equal(km.cluster_assignment, g_adni["km_assign"])
+    assert relerr(km._packed_params(), g_adni["km_params"]) < RTOL
+    best, obj = proto.train_with_multiple_random_starts(n_starts=int(g_adni["n_starts"]), use_cache=False,
+                                                        return_objectives=True)
+    assert relerr(obj, g_adni["objectives"]) < RTOL
+    assert best.random_seed == int(g_adni["best_seed"])
+    assert np.array_equal(best.cluster_assignment, g_adni["best_assign"])
+    assert relerr(best._packed_params(), g_adni["best_params"]) < RTOL
+    a, pr, pn = best.mle_cluster_assignment(states=zte, observations=xte, return_probs=True,
+                                            return_prenormalized_log_probs=True)
+    assert np.array_equal(a, g_adni["te_assign"])
+    assert relerr(pr, g_adni["te_probs"]) < RTOL
+    assert relerr(pn, g_adni["te_prenorm"]) < RTOL
+    mask0 = lambda arr: np.concatenate([arr[:1], np.full_like(arr[1:], np.nan)], axis=0)
+    a0, p0 = best.mle_cluster_assignment(states=mask0(zte), observations=mask0(xte), return_probs=True)
+    assert np.array_equal(a0, g_adni["te0_assign"])
+    assert relerr(p0, g_adni["te0_probs"]) < RTOL
+    snap = lambda arr: np.concatenate([np.where(np.arange(arr.shape[0])[:, None, None] == i, arr, np.nan)
+                                       for i in range(arr.shape[0])], axis=1)
+    zp, xp = snap(zte), snap(xte)
+    assert np.array_equal(best.mle_cluster_assignment(states=zp, observations=xp), g_adni["te_snap_assign"])
+    assert relerr(best.cluster_assignment_index(states=zp, observations=xp), g_adni["te_snap_index"]) < RTOL
+    assert np.array_equal(best.mle_cluster_assignment(states=np.nan * np.ones_like(zp), observations=xp),
+                          g_adni["te_snapx_assign"])
+    znh = np.nan * np.ones_like(zte)
+    assert np.array_equal(best.mle_cluster_assignment(states=znh, observations=xte), g_adni["te_nohid_assign"])
+    assert relerr(best.cluster_assignment_index(states=znh, observations=xte), g_adni["te_nohid_index"]) < RTOL
+    assert np.array_equal(best.observations_mle_cluster_assignment(observations=xte), g_adni["te_obs_assign"])
+
+
+# -------------------------------------------------------------------------------------------------
+# against the CPU oracle on fresh seeded inputs, and size-independent properties at scale
+# -------------------------------------------------------------------------------------------------
+
+
+def _synthetic(n, T, d, l, n_c, seed, p_missing=0.2, sep=0.3):
+    rng = np.random.default_rng(seed)
+
+    def spd(k):
+        B = rng.normal(size=(k, k))
+        return B @ B.T / k + 0.3 * np.eye(k)
+
+    def comp():
+        return dict(m=2 * rng.normal(size=d), S=spd(d), A=rng.normal(scale=0.5, size=(d, d)), G=spd(d),
+                    H=rng.normal(size=(d, l)), L=spd(l))
+
+    base = comp()
+    comps = []
+    for _ in range(n_c):
+        p = comp()
+        comps.append({k: base[k] + sep * (p[k] - base[k]) for k in base})
+    lab = rng.integers(0, n_c, size=n)
+    z, x = np.empty((T, n, d)), np.empty((T, n, l))
+    for c, p in enumerate(comps):
+        idx = np.flatnonzero(lab == c)
+        cs, cg, cl = (np.linalg.cholesky(p[k]) for k in ("S", "G", "L"))
+        zc = np.empty((T, idx.size, d))
+        zc[0] = p["m"] + rng.normal(size=(idx.size, d)) @ cs.T
+        for t in range(T):
+            if t:
+                zc[t] = zc[t - 1] @ p["A"] + rng.normal(size=(idx.size, d)) @ cg.T
+            x[t, idx] = zc[t] @ p["H"] + rng.normal(size=(idx.size, l)) @ cl.T
+        z[:, idx] = zc
+    z[rng.random(z.shape) < p_missing] = np.nan
+    x[rng.random(x.shape) < p_missing] = np.nan
+    return z, x
+
+
+@pytest.mark.parametrize("shape", [(8, 4, 4, 4, 30011), (4, 2, 4, 4, 7777), (6, 3, 5, 3, 4099), (3, 6, 2, 2, 2500)])
+def test_fit_vs_oracle(mix, shape):
+    """Whole EM fits against the oracle (numpy M-step + C E-step) on inputs the goldens do not
+    cover: ragged n (not a multiple of the 128-trajectory tile), generic-dimension kernels."""
+    from oracle import cport as oc
+    from oracle import dense as od
+
+    T, d, l, n_c, n = shape
+    z, x = _synthetic(n, T, d, l, n_c, seed=n)
+    a0 = od.random_init(n, n_c, 11)
+    ref = od.train(z, x, a0, n_c, alpha=0.0, n_steps=6, e_step_fn=oc.e_step_seq)
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=n_c, states=z, observations=x, random_seed=11)
+    mdl.train(n_steps=6)
+    assert mdl.fit_info["switches"] == ref.switches
+    assert np.array_equal(mdl.cluster_assignment, ref.assign)
+    assert relerr(mdl._packed_params(), ref.params.packed()) < RTOL
+    # dense (reference-formulation) check of the final log-likelihoods on a sample
+    sub = slice(0, 400)
+    lld = oc.dense_loglik_matrix(ref.params, z[:, sub], x[:, sub])
+    assert relerr(mdl.log_likelihood_matrix(states=z[:, sub], observations=x[:, sub]), lld) < RTOL
+
+
+def test_scale_properties(mix, eng):
+    """config-2 size (1M trajectories, T=8, d=l=4, n_c=4): properties that do not need an oracle
+    pass at full size, plus an oracle check on a strided sample."""
+    import mtm_b200
+    from oracle import cport as oc
+
+    n, T, d, l, n_c = 1_000_000, 8, 4, 4, 4
+    zs, xs = _synthetic(50_000, T, d, l, n_c, seed=5)
+    reps = n // zs.shape[1]
+    z = np.ascontiguousarray(np.tile(zs, (1, reps, 1)))
+    x = np.ascontiguousarray(np.tile(xs, (1, reps, 1)))
+    rng = np.random.default_rng(0)
+    # break the exact periodicity of the tiling with fresh missingness
+    z[rng.random(z.shape) < 0.02] = np.nan
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=n_c, states=z, observations=x, random_seed=42)
+    mdl.train(n_steps=3)
+    assert mdl.fit_info["n_e_steps"] == 3
+    P = mdl._packed_params()
+    data = mdl._train_data()
+    res = eng.estep(data, P, n_c, T, want_ll=True)
+    ll = res["ll"].cpu().numpy()
+    a = res["assign"].cpu().numpy()
+    # (a) oracle on a strided sample of the full-size run
+    idx = np.arange(0, n, 97)[:8000]
+    llo = oc.seq_loglik_matrix(P, z[:, idx], x[:, idx])
+    assert relerr(ll[:, idx], llo) < RTOL
+    assert np.array_equal(a[idx], oc.assign(llo, P[:, 0]))
+    # (b) permutation equivariance: shuffling trajectories shuffles the outputs
+    perm = rng.permutation(n)
+    dp = mtm_b200.DeviceData(z[:, perm], x[:, perm], eng.device)
+    rp = eng.estep(dp, P, n_c, T, want_ll=True)
+    assert np.array_equal(rp["ll"].cpu().numpy(), ll[:, perm])
+    assert np.array_equal(rp["assign"].cpu().numpy(), a[perm])
+    # (c) switch count = number of changed labels; cluster sizes consistent
+    old = torch.from_numpy(rng.integers(0, n_c, n).astype(np.int32)).to(eng.device)
+    old_h = old.cpu().numpy().copy()
+    r2 = eng.estep(data, P, n_c, T, assign=old, count_switches=True)
+    assert r2["n_switches"] == int(np.sum(old_h != a))
+    assert r2["min_count"] == int(np.bincount(a, minlength=n_c).min())
+    # (d) hidden states all NaN through the joint kernel == observation-only kernel
+    zn = mtm_b200.DeviceData(np.full((T, 4096, d), np.nan), x[:, :4096], eng.device)
+    xo = mtm_b200.DeviceData(None, x[:, :4096], eng.device)
+    l1 = eng.estep(zn, P, n_c, T, want_ll=True)["ll"].cpu().numpy()
+    l2 = eng.estep(xo, P, n_c, T, want_ll=True, d=d)["ll"].cpu().numpy()
+    assert relerr(l1, l2) < 1e-13
+    # (e) statistics are additive over shards (what the multi-GPU all-reduce relies on)
+    at = torch.from_numpy(a.astype(np.int32)).to(eng.device)
+    full = eng.mstats(data, at, n_c).cpu().numpy()
+    h = n // 2 + 13
+    d1 = mtm_b200.DeviceData(z[:, :h], x[:, :h], eng.device)
+    d2 = mtm_b200.DeviceData(z[:, h:], x[:, h:], eng.device)
+    s1 = eng.mstats(d1, at[:h].contiguous(), n_c).cpu().numpy()
+    s2 = eng.mstats(d2, at[h:].contiguous(), n_c).cpu().numpy()
+    assert relerr(s1 + s2, full) < 1e-12
+    # counts inside the statistics are exact
+    assert np.array_equal(full[:, 0], np.bincount(a, minlength=n_c).astype(float))
+    # (f) M-step from the statistics == numpy M-step of the oracle on a sample-sized problem
+    pf, _ = eng.finalize(torch.from_numpy(full).to(eng.device), n_c, d, l, n, 0.0)
+    p2, _, st = eng.mstep(data, at, n_c, 0.0)
+    assert st == 0 and np.array_equal(pf.cpu().numpy(), p2.cpu().numpy())
+
+
+def test_edge_inputs(mix, eng):
+    import mtm_b200
+    from oracle import cport as oc
+
+    z, x = _synthetic(300, 5, 4, 4, 3, seed=3)
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=3, states=z, observations=x, random_seed=1)
+    mdl.train(n_steps=4)
+    P = mdl._packed_params()
+    for n in (1, 31, 127, 128, 129, 300):
+        for T0 in (1, 5):
+            got = mdl.log_likelihood_matrix(states=z[:, :n], observations=x[:, :n], T0=T0)
+            assert relerr(got, oc.seq_loglik_matrix(P, z[:, :n], x[:, :n], T0=T0)) < RTOL
+    # a single time step (T = 1) and +-inf entries
+    z1, x1 = z[:1].copy(), x[:1].copy()
+    z1[0, 0, 0], x1[0, 1, 2] = np.inf, -np.inf
+    got = mdl.log_likelihood_matrix(states=z1, observations=x1, T0=1)
+    assert relerr(got, oc.seq_loglik_matrix(P, z1, x1)) < RTOL
+    # near-empty cluster before the first M-step: nothing runs (MMM:1328-1336)
+    m2 = mix.MMLinGaussSS_marginalizable(n_clusters=3, states=z, observations=x, random_seed=1)
+    m2.cluster_assignment = np.r_[np.zeros(150, int), np.ones(147, int), 2 * np.ones(3, int)]
+    before = m2._packed_params().copy()
+    m2.train()
+    assert m2.fit_info["exit"] == "guard0" and m2.last_trained is None
+    assert np.array_equal(m2._packed_params(), before)
+    # n_steps = 0: guard + one M-step, no E-step
+    m3 = mix.MMLinGaussSS_marginalizable(n_clusters=3, states=z, observations=x, random_seed=1)
+    m3.train(n_steps=0)
+    assert m3.fit_info["n_e_steps"] == 0 and m3.fit_info["n_m_steps"] == 1
+    # non-finite covariance -> the reference's LinAlgError
+    m3.init_state_covs[1][0, 0] = np.nan
+    with pytest.raises(np.linalg.LinAlgError):
+        m3.mle_cluster_assignment()
+    # regress / regress_alpha (MMM:1167-1233) against numpy
+    rng = np.random.default_rng(9)
+    X, B = rng.normal(size=(500, 3)), rng.normal(size=(3, 2))
+    Y = X @ B + 0.1 * rng.normal(size=(500, 2))
+    for alpha in (0.0, 0.7):
+        Bh, Sh = mix.MMLinGaussSS_marginalizable.regress_alpha(X, Y, alpha)
+        Bn = np.linalg.solve(X.T @ X + alpha * np.eye(3), X.T @ Y)
+        assert relerr(Bh, Bn) < RTOL
+        assert relerr(Sh, np.cov(Y - X @ Bn, rowvar=False)) < RTOL
+
+
+def test_pickle_roundtrip(mix, tmp_path):
+    z, x = _synthetic(200, 4, 2, 3, 2, seed=8)
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=2, states=z, observations=x, random_seed=3).train(n_steps=5)
+    mdl.to_pickle(save_location=str(tmp_path))
+    mdl.to_pickle(save_location=str(tmp_path))
+    files = list(tmp_path.glob(f"mmm-{mdl.hex_hash}*"))
+    assert len(files) == 1  # "there can only be one" (MMM:237-245)
+    back = mix.MMLinGaussSS_marginalizable.from_pickle(str(files[0]), training_data={"states": z, "observations": x})
+    assert back.hex_hash == mdl.hex_hash
+    assert np.array_equal(back._packed_params(), mdl._packed_params())
+    assert np.array_equal(back.mle_cluster_assignment(), mdl.mle_cluster_assignment())
