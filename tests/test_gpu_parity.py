@@ -84,10 +84,12 @@ def test_em_trace(g_em, mix, key):
     assert np.array_equal(mdl.cluster_assignment, g_em[f"{key}_assign"])
     assert mdl.cluster_assignment.dtype == np.int64
     assert relerr(mdl._packed_params(), g_em[f"{key}_params"]) < RTOL
-    expect_exit = {"short": "exhausted", "guardexit": "guard"}.get(key, "converged")
+    sw = list(g_em[f"{key}_switches"])
+    expect_exit = "converged" if sw[-1] == 0 else ("exhausted" if len(sw) == c["n_steps"] else "guard")
     assert info["exit"] == expect_exit
-    if key == "guardexit":
-        return
+    assert {"short": "exhausted", "guardexit": "guard", "c2s": "converged"}.get(key, expect_exit) == expect_exit
+    if expect_exit == "guard":
+        return  # parameters are those of the previous M-step; nothing else was stored
     # outputs of the trained model
     a, probs, prenorm = mdl.mle_cluster_assignment(return_probs=True, return_prenormalized_log_probs=True)
     assert np.array_equal(a, g_em[f"{key}_mle_assign"])
