@@ -11,7 +11,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmtm_b200.so")
+# MTM_B200_LIB: alternative build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("MTM_B200_LIB") or os.path.join(HERE, "libmtm_b200.so")
 
 MTM_MAX_DIM = 8
 MTM_MAX_CLUSTERS = 64

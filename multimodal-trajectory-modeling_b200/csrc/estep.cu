@@ -18,8 +18,12 @@
 
 namespace mtm {
 
+#ifndef MTM_E_MINBLOCKS
+#define MTM_E_MINBLOCKS 2
+#endif
+
 template <int D_, int L_, bool HAS_Z>
-__global__ void __launch_bounds__(kEThreads) estep_kernel(const EStepArgs a) {
+__global__ void __launch_bounds__(kEThreads, MTM_E_MINBLOCKS) estep_kernel(const EStepArgs a) {
     using DM = Dims<D_, L_>;
     const DM dm{a.d, a.l};
     if (a.check_done && a.ctrl->done) return;
