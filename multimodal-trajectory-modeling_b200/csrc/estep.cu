@@ -14,37 +14,65 @@
 // thread hit L1/L2.  Parameters (n_c x 85 doubles at d=l=4) sit in shared memory and are read
 // as warp-uniform broadcasts.
 #include "common.cuh"
+#define MTM_DEFINE_CONST_PARAMS
 #include "filter.cuh"
 
 namespace mtm {
 
-#ifndef MTM_E_MINBLOCKS
-#define MTM_E_MINBLOCKS 2
+// NOTE: max-threads-only launch bounds on purpose.  With a min-blocks argument ptxas (12.9) keeps the
+// model parameters in vector registers (LDC R, c[3][R+imm]); without it they go through the uniform
+// datapath (LDCU.64 UR, c[3][UR+imm] -> DFMA R, R, UR, R), which is what lifts the register-file
+// read-bandwidth limit on the DFMA stream (profiles/r1a_dfma_probe.txt).
+#ifdef MTM_E_MINBLOCKS
+#define MTM_E_BOUNDS __launch_bounds__(kEThreads, MTM_E_MINBLOCKS)
+#else
+#define MTM_E_BOUNDS __launch_bounds__(kEThreads)
 #endif
 
-template <int D_, int L_, bool HAS_Z>
-__global__ void __launch_bounds__(kEThreads, MTM_E_MINBLOCKS) estep_kernel(const EStepArgs a) {
+// parameter source of cluster c: constant bank (CONSTP) or the block's shared-memory copy
+template <bool CONSTP>
+struct PSel;
+template <>
+struct PSel<true> {
+    using type = ConstSrc;
+    static __device__ __forceinline__ ConstSrc get(const double *, int c, int stride) { return ConstSrc{c * stride}; }
+};
+template <>
+struct PSel<false> {
+    using type = SmemSrc;
+    static __device__ __forceinline__ SmemSrc get(const double *s_par, int c, int stride) {
+        return SmemSrc{s_par + c * stride};
+    }
+};
+
+template <int D_, int L_, bool HAS_Z, bool CONSTP>
+__global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     using DM = Dims<D_, L_>;
+    using PS = PSel<CONSTP>;
     const DM dm{a.d, a.l};
     if (a.check_done && a.ctrl->done) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int stride = dm.stride();
-    double *s_par = reinterpret_cast<double *>(smem_raw);                 // n_c * stride
-    double *s_logpi = s_par + a.n_c * stride;                             // n_c
-    uint32_t *s_fin = reinterpret_cast<uint32_t *>(s_logpi + a.n_c);      // n_c * T0
+    double *s_par = reinterpret_cast<double *>(smem_raw);                 // n_c * stride (unused if CONSTP)
+    double *s_logpi = s_par + (CONSTP ? 0 : a.n_c * stride);              // n_c
+    double *s_pi = s_logpi + a.n_c;                                       // n_c
+    uint32_t *s_fin = reinterpret_cast<uint32_t *>(s_pi + a.n_c);         // n_c * T0
     unsigned int *s_cnt = s_fin + a.n_c * a.T0;                           // n_c
     __shared__ double s_red[2][kEThreads / 32];
     __shared__ unsigned int s_sw;
 
     const int tid = threadIdx.x;
-    for (int k = tid; k < a.n_c * stride; k += kEThreads) s_par[k] = a.params[k];
+    if (!CONSTP)
+        for (int k = tid; k < a.n_c * stride; k += kEThreads) s_par[k] = a.params[k];
     for (int k = tid; k < a.n_c; k += kEThreads) s_cnt[k] = 0;
     if (tid == 0) s_sw = 0;
     __syncthreads();
     for (int c = tid; c < a.n_c; c += kEThreads) {
-        s_logpi[c] = log(s_par[c * stride]);
-        mean_finite_masks(dm, s_par + c * stride, a.T0, s_fin + c * a.T0);
+        const auto src = PS::get(s_par, c, stride);
+        s_pi[c] = src[0];
+        s_logpi[c] = log(src[0]);
+        mean_finite_masks(dm, src, a.T0, s_fin + c * a.T0);
     }
     __syncthreads();
 
@@ -65,9 +93,9 @@ __global__ void __launch_bounds__(kEThreads, MTM_E_MINBLOCKS) estep_kernel(const
         double best = 0.0, best_ll = 0.0, sum_l = 0.0;
         int arg = 0;
         for (int c = 0; c < a.n_c; ++c) {
-            const double ll = filter_eval<DM, HAS_Z>(dm, z_i, zs, x_i, xs, a.T0, s_par + c * stride,
+            const double ll = filter_eval<DM, HAS_Z>(dm, z_i, zs, x_i, xs, a.T0, PS::get(s_par, c, stride),
                                                      s_fin + c * a.T0, bad);
-            const double lc = s_par[c * stride] * exp(ll);
+            const double lc = s_pi[c] * exp(ll);
             if (valid) {
                 if (a.ll) a.ll[(int64_t)c * n + i] = ll;
                 if (a.prenorm) a.prenorm[(int64_t)c * n + i] = s_logpi[c] + ll;
@@ -165,7 +193,7 @@ __global__ void score_reduce_kernel(const double *__restrict__ partials, int gri
 }
 
 size_t estep_smem(int n_c, int T0, int d, int l) {
-    return (size_t)n_c * param_stride(d, l) * 8 + (size_t)n_c * 8 + (size_t)n_c * T0 * 4 + (size_t)n_c * 4 + 16;
+    return (size_t)n_c * param_stride(d, l) * 8 + (size_t)n_c * 16 + (size_t)n_c * T0 * 4 + (size_t)n_c * 4 + 16;
 }
 
 int estep_grid(int64_t n, int sm_count) {
@@ -176,32 +204,48 @@ int estep_grid(int64_t n, int sm_count) {
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
+template <int D_, int L_, bool HAS_Z, bool CONSTP>
+static cudaError_t launch_one(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
+    auto k = estep_kernel<D_, L_, HAS_Z, CONSTP>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, kEThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <int D_, int L_>
 static cudaError_t launch_dl(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
-    if (a.z) {
-        auto k = estep_kernel<D_, L_, true>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, kEThreads, smem, s>>>(a);
-    } else {
-        auto k = estep_kernel<D_, L_, false>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, kEThreads, smem, s>>>(a);
+    const size_t n_par = (size_t)a.n_c * param_stride(a.d, a.l);
+    if (D_ > 0 && n_par <= MTM_CONST_DOUBLES) {
+        // stage the parameter rows in the constant bank (device -> device, stream ordered)
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_par, a.params, n_par * sizeof(double), 0,
+                                                cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return e;
+        return a.z ? launch_one<D_, L_, true, true>(a, grid, smem, s) : launch_one<D_, L_, false, true>(a, grid, smem, s);
     }
-    return cudaGetLastError();
+    return a.z ? launch_one<D_, L_, true, false>(a, grid, smem, s) : launch_one<D_, L_, false, false>(a, grid, smem, s);
 }
 
 cudaError_t launch_estep(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
 #define MTM_CASE(DD, LL) \
     if (a.d == DD && a.l == LL) return launch_dl<DD, LL>(a, grid, smem, s);
     MTM_CASE(4, 4)
+#ifndef MTM_ONLY_44
     MTM_CASE(2, 4)
     MTM_CASE(2, 3)
     MTM_CASE(1, 1)
     MTM_CASE(3, 3)
     MTM_CASE(2, 2)
     MTM_CASE(5, 3)
+#endif
 #undef MTM_CASE
+#ifdef MTM_ONLY_44
+    return cudaErrorInvalidValue;
+#else
     return launch_dl<0, 0>(a, grid, smem, s);  // generic run-time dimensions
+#endif
 }
 
 cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, cudaStream_t s) {

@@ -63,20 +63,48 @@ __device__ __forceinline__ double fast_rcp(double s) {
     return r;
 }
 
-// pointers into one packed parameter row [pi | m | S | A | G | H | Lam]
-template <class DM>
+// Where the packed parameter rows [pi | m | S | A | G | H | Lam] live.
+//  * ConstSrc: __constant__ memory, indexed with a warp-uniform offset.  The compiler fetches such
+//    operands through the uniform datapath (ULDC) and feeds them to DFMA as uniform-register
+//    operands, so a DFMA that multiplies by a model parameter reads only TWO vector registers and
+//    issues at the full FP64 rate (tools/dfma_probe.cu: 34-35.7 TFLOP/s vs 24.6 with three vector
+//    sources, 27-31 when the parameter first goes through a vector register via shared memory).
+//  * SmemSrc: shared memory (fallback when n_c * stride exceeds the constant bank, and for the
+//    generic run-time-dimension instantiation).
+#ifndef MTM_CONST_DOUBLES
+#define MTM_CONST_DOUBLES 7680  // 60 KB of the 64 KB constant bank
+#endif
+#ifdef MTM_DEFINE_CONST_PARAMS
+__constant__ double c_par[MTM_CONST_DOUBLES];
+struct ConstSrc {
+    int base;
+    __device__ __forceinline__ double operator[](int k) const { return c_par[base + k]; }
+};
+#endif
+struct SmemSrc {
+    const double *row;
+    __device__ __forceinline__ double operator[](int k) const { return row[k]; }
+};
+
+template <class DM, class PS>
 struct ParamView {
-    const double *pi, *m, *S, *A, *G, *H, *Lam;
-    __device__ __forceinline__ ParamView(const DM &dm, const double *row) {
+    PS ps;
+    int oS, oA, oG, oH, oL;
+    __device__ __forceinline__ ParamView(const DM &dm, const PS &src) : ps(src) {
         const int d = dm.d(), l = dm.l();
-        pi = row;
-        m = row + 1;
-        S = m + d;
-        A = S + d * d;
-        G = A + d * d;
-        H = G + d * d;
-        Lam = H + d * l;
+        oS = 1 + d;
+        oA = oS + d * d;
+        oG = oA + d * d;
+        oH = oG + d * d;
+        oL = oH + d * l;
     }
+    __device__ __forceinline__ double pi() const { return ps[0]; }
+    __device__ __forceinline__ double m(int k) const { return ps[1 + k]; }
+    __device__ __forceinline__ double S(int k) const { return ps[oS + k]; }
+    __device__ __forceinline__ double A(int k) const { return ps[oA + k]; }
+    __device__ __forceinline__ double G(int k) const { return ps[oG + k]; }
+    __device__ __forceinline__ double H(int k) const { return ps[oH + k]; }
+    __device__ __forceinline__ double Lam(int k) const { return ps[oL + k]; }
 };
 
 template <class DM>
@@ -96,16 +124,16 @@ __device__ __forceinline__ double symget(const M &P, int i, int j) {
     return i <= j ? P[i][j] : P[j][i];
 }
 
-template <class DM>
-__device__ __forceinline__ void filter_init(const DM &dm, FilterState<DM> &f, const ParamView<DM> &p) {
+template <class DM, class PV>
+__device__ __forceinline__ void filter_init(const DM &dm, FilterState<DM> &f, const PV &p) {
     const int d = dm.d();
     MTM_UNROLL
     for (int i = 0; i < DM::DM; ++i) {
         if (i < d) {
-            f.mu[i] = p.m[i];
+            f.mu[i] = p.m(i);
             MTM_UNROLL
             for (int j = i; j < DM::DM; ++j)
-                if (j < d) f.P[i][j] = p.S[i * d + j];
+                if (j < d) f.P[i][j] = p.S(i * d + j);
         }
     }
     f.q = 0.0;
@@ -116,32 +144,40 @@ __device__ __forceinline__ void filter_init(const DM &dm, FilterState<DM> &f, co
 }
 
 // (mu, P) <- (mu A, A' P A + Gamma)     [SSM:62-64 for P, :312-314 for mu]
-template <class DM>
-__device__ __forceinline__ void filter_propagate(const DM &dm, FilterState<DM> &f, const ParamView<DM> &p) {
+//
+// All small products below are written in "outer-product order": the innermost loop runs over
+// independent accumulators that share ONE multiplicand.  Consecutive DFMAs then (a) are independent
+// (no latency chain) and (b) keep that multiplicand in the operand-reuse cache, which matters on
+// this part: a DFMA reading three distinct vector registers issues at 72 % of the FP64 peak, one
+// with a reused operand at 92 % (tools/dfma_probe.cu).
+template <class DM, class PV>
+__device__ __forceinline__ void filter_propagate(const DM &dm, FilterState<DM> &f, const PV &p) {
     const int d = dm.d();
     double nmu[DM::DM];
     double PA[DM::DM][DM::DM];
     MTM_UNROLL
-    for (int j = 0; j < DM::DM; ++j) {
-        if (j < d) {
-            double s = 0.0;
+    for (int j = 0; j < DM::DM; ++j) nmu[j] = 0.0;
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            const double mi = f.mu[i];
             MTM_UNROLL
-            for (int i = 0; i < DM::DM; ++i)
-                if (i < d) s = fma(f.mu[i], p.A[i * d + j], s);
-            nmu[j] = s;
+            for (int j = 0; j < DM::DM; ++j)
+                if (j < d) nmu[j] = fma(mi, p.A(i * d + j), nmu[j]);
         }
     }
     MTM_UNROLL
     for (int i = 0; i < DM::DM; ++i) {
         if (i < d) {
             MTM_UNROLL
-            for (int j = 0; j < DM::DM; ++j) {
-                if (j < d) {
-                    double s = 0.0;
+            for (int j = 0; j < DM::DM; ++j) PA[i][j] = 0.0;
+            MTM_UNROLL
+            for (int a = 0; a < DM::DM; ++a) {
+                if (a < d) {
+                    const double pia = symget(f.P, i, a);
                     MTM_UNROLL
-                    for (int a = 0; a < DM::DM; ++a)
-                        if (a < d) s = fma(symget(f.P, i, a), p.A[a * d + j], s);
-                    PA[i][j] = s;
+                    for (int j = 0; j < DM::DM; ++j)
+                        if (j < d) PA[i][j] = fma(pia, p.A(a * d + j), PA[i][j]);
                 }
             }
         }
@@ -151,13 +187,15 @@ __device__ __forceinline__ void filter_propagate(const DM &dm, FilterState<DM> &
         if (i < d) {
             f.mu[i] = nmu[i];
             MTM_UNROLL
-            for (int j = i; j < DM::DM; ++j) {
-                if (j < d) {
-                    double s = p.G[i * d + j];
+            for (int j = i; j < DM::DM; ++j)
+                if (j < d) f.P[i][j] = p.G(i * d + j);
+            MTM_UNROLL
+            for (int a = 0; a < DM::DM; ++a) {
+                if (a < d) {
+                    const double aai = p.A(a * d + i);
                     MTM_UNROLL
-                    for (int a = 0; a < DM::DM; ++a)
-                        if (a < d) s = fma(p.A[a * d + i], PA[a][j], s);
-                    f.P[i][j] = s;
+                    for (int j = i; j < DM::DM; ++j)
+                        if (j < d) f.P[i][j] = fma(aai, PA[a][j], f.P[i][j]);
                 }
             }
         }
@@ -210,34 +248,36 @@ __device__ __forceinline__ void filter_condition_z(const DM &dm, FilterState<DM>
 }
 
 // predictive of x_t and conditioning on its present coordinates   [SSM:161-166, 217-222, 337-339]
-template <class DM>
-__device__ __forceinline__ void filter_condition_x(const DM &dm, FilterState<DM> &f, const ParamView<DM> &p,
+template <class DM, class PV>
+__device__ __forceinline__ void filter_condition_x(const DM &dm, FilterState<DM> &f, const PV &p,
                                                    const double (&xt)[DM::LM], uint32_t finmask) {
     const int d = dm.d(), l = dm.l();
     double mux[DM::LM];
     double C[DM::DM][DM::LM];   // Cov(z_t, x_t | past) = P H
     double Sx[DM::LM][DM::LM];  // Var(x_t | past) = H' P H + Lambda, upper triangle
     MTM_UNROLL
-    for (int b = 0; b < DM::LM; ++b) {
-        if (b < l) {
-            double s = 0.0;
+    for (int b = 0; b < DM::LM; ++b) mux[b] = 0.0;
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            const double mi = f.mu[i];
             MTM_UNROLL
-            for (int i = 0; i < DM::DM; ++i)
-                if (i < d) s = fma(f.mu[i], p.H[i * l + b], s);
-            mux[b] = s;
+            for (int b = 0; b < DM::LM; ++b)
+                if (b < l) mux[b] = fma(mi, p.H(i * l + b), mux[b]);
         }
     }
     MTM_UNROLL
     for (int i = 0; i < DM::DM; ++i) {
         if (i < d) {
             MTM_UNROLL
-            for (int b = 0; b < DM::LM; ++b) {
-                if (b < l) {
-                    double s = 0.0;
+            for (int b = 0; b < DM::LM; ++b) C[i][b] = 0.0;
+            MTM_UNROLL
+            for (int a = 0; a < DM::DM; ++a) {
+                if (a < d) {
+                    const double pia = symget(f.P, i, a);
                     MTM_UNROLL
-                    for (int a = 0; a < DM::DM; ++a)
-                        if (a < d) s = fma(symget(f.P, i, a), p.H[a * l + b], s);
-                    C[i][b] = s;
+                    for (int b = 0; b < DM::LM; ++b)
+                        if (b < l) C[i][b] = fma(pia, p.H(a * l + b), C[i][b]);
                 }
             }
         }
@@ -246,13 +286,15 @@ __device__ __forceinline__ void filter_condition_x(const DM &dm, FilterState<DM>
     for (int a = 0; a < DM::LM; ++a) {
         if (a < l) {
             MTM_UNROLL
-            for (int b = a; b < DM::LM; ++b) {
-                if (b < l) {
-                    double s = p.Lam[a * l + b];
+            for (int b = a; b < DM::LM; ++b)
+                if (b < l) Sx[a][b] = p.Lam(a * l + b);
+            MTM_UNROLL
+            for (int i = 0; i < DM::DM; ++i) {
+                if (i < d) {
+                    const double hia = p.H(i * l + a);
                     MTM_UNROLL
-                    for (int i = 0; i < DM::DM; ++i)
-                        if (i < d) s = fma(p.H[i * l + a], C[i][b], s);
-                    Sx[a][b] = s;
+                    for (int b = a; b < DM::LM; ++b)
+                        if (b < l) Sx[a][b] = fma(hia, C[i][b], Sx[a][b]);
                 }
             }
         }
@@ -336,11 +378,11 @@ __device__ __forceinline__ void load_row(const double *__restrict__ p, double (&
 
 // One full evaluation.  z_i / x_i point at step 0 of trajectory i; zs / xs = step strides in doubles.
 // fin[t] = bit mask of finite unconditional means at step t: bits [0, d) for z, [16, 16 + l) for x.
-template <class DM, bool HAS_Z>
+template <class DM, bool HAS_Z, class PS>
 __device__ __forceinline__ double filter_eval(const DM &dm, const double *__restrict__ z_i, int64_t zs,
                                               const double *__restrict__ x_i, int64_t xs, int T0,
-                                              const double *prow, const uint32_t *fin, int &bad) {
-    const ParamView<DM> p(dm, prow);
+                                              const PS &psrc, const uint32_t *fin, int &bad) {
+    const ParamView<DM, PS> p(dm, psrc);
     FilterState<DM> f;
     filter_init(dm, f, p);
     double zt[DM::DM], xt[DM::LM];
@@ -368,17 +410,17 @@ __device__ __forceinline__ double filter_eval(const DM &dm, const double *__rest
 
 // finiteness masks of the unconditional stacked mean [m A^t | m A^t H] for one cluster; run by one
 // thread per cluster in a kernel prologue.  T0 words.
-template <class DM>
-__device__ void mean_finite_masks(const DM &dm, const double *prow, int T0, uint32_t *fin) {
-    const ParamView<DM> p(dm, prow);
+template <class DM, class PS>
+__device__ void mean_finite_masks(const DM &dm, const PS &psrc, int T0, uint32_t *fin) {
+    const ParamView<DM, PS> p(dm, psrc);
     const int d = dm.d(), l = dm.l();
     double mu[MTM_MAX_DIM], nm[MTM_MAX_DIM];
-    for (int i = 0; i < d; ++i) mu[i] = p.m[i];
+    for (int i = 0; i < d; ++i) mu[i] = p.m(i);
     for (int t = 0; t < T0; ++t) {
         if (t > 0) {
             for (int j = 0; j < d; ++j) {
                 double s = 0.0;
-                for (int i = 0; i < d; ++i) s = fma(mu[i], p.A[i * d + j], s);
+                for (int i = 0; i < d; ++i) s = fma(mu[i], p.A(i * d + j), s);
                 nm[j] = s;
             }
             for (int j = 0; j < d; ++j) mu[j] = nm[j];
@@ -387,7 +429,7 @@ __device__ void mean_finite_masks(const DM &dm, const double *prow, int T0, uint
         for (int j = 0; j < d; ++j) m |= finite_bits(mu[j]) ? (1u << j) : 0u;
         for (int b = 0; b < l; ++b) {
             double s = 0.0;
-            for (int i = 0; i < d; ++i) s = fma(mu[i], p.H[i * l + b], s);
+            for (int i = 0; i < d; ++i) s = fma(mu[i], p.H(i * l + b), s);
             m |= finite_bits(s) ? (1u << (16 + b)) : 0u;
         }
         fin[t] = m;

@@ -5,16 +5,24 @@
 namespace mtm {
 
 constexpr int kChains = 8;
+__constant__ double c_peak_tab[64];
 
-__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b) {
-    double x[kChains];
+// Each DFMA reads two vector registers and one uniform-register operand shared by the 8 independent
+// chains — the best-case operand mix (35.7 TFLOP/s on this part; a chain with constant-bank a and b
+// measures 34.1, three distinct vector sources 24.6: tools/dfma_probe.cu).
+__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, int base) {
+    double x[kChains], y[kChains];
 #pragma unroll
-    for (int k = 0; k < kChains; ++k) x[k] = (double)(threadIdx.x + k) * 1e-3;
+    for (int k = 0; k < kChains; ++k) {
+        x[k] = (double)(threadIdx.x + k) * 1e-3;
+        y[k] = 1.0 - (double)(threadIdx.x + k) * 1e-9;
+    }
     for (int it = 0; it < iters; ++it) {
+        const double *t = c_peak_tab + base + (it & 7) * 8;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
 #pragma unroll
-            for (int k = 0; k < kChains; ++k) x[k] = fma(x[k], a, b);
+            for (int k = 0; k < kChains; ++k) x[k] = fma(y[(k + u) % kChains], t[u], x[k]);
         }
     }
     double s = 0.0;
@@ -34,7 +42,7 @@ cudaError_t run_fp64_peak(int reps, int sm_count, cudaStream_t s, double *tflops
     double best_ms = 1e30;
     for (int r = 0; r < reps + 2; ++r) {  // two warm-up launches
         cudaEventRecord(t0, s);
-        dfma_kernel<<<grid, threads, 0, s>>>(out, iters, 0.999999, 1e-9);
+        dfma_kernel<<<grid, threads, 0, s>>>(out, iters, 0);
         cudaEventRecord(t1, s);
         e = cudaEventSynchronize(t1);
         if (e != cudaSuccess) break;

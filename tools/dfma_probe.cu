@@ -75,6 +75,40 @@ __global__ void __launch_bounds__(256) k_smem(double *out, int iters, const doub
     if (s == 123.456) out[threadIdx.x] = s;
 }
 
+// (f) one source from __constant__[uniform idx], each constant shared by NS consecutive DFMAs
+template <int NS>
+__global__ void __launch_bounds__(256) k_cshare(double *out, int iters, const double *in, int base) {
+    double x[K], y[K];
+    for (int k = 0; k < K; ++k) { x[k] = in[threadIdx.x + k]; y[k] = in[threadIdx.x + 8 + k]; }
+    for (int it = 0; it < iters; ++it) {
+        const double *t = c_tab + base + (it & 7) * 64;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) x[k] = fma(y[(k + u) % K], t[u * (K / NS) + k / NS], x[k]);
+    }
+    double s = 0; for (int k = 0; k < K; ++k) s += x[k];
+    if (s == 123.456) out[threadIdx.x] = s;
+}
+// (g) same sharing pattern but the shared operand comes from shared memory (LDS into a vector register)
+template <int NS>
+__global__ void __launch_bounds__(256) k_sshare(double *out, int iters, const double *in, int base) {
+    __shared__ double tab[1024];
+    for (int k = threadIdx.x; k < 1024; k += 256) tab[k] = in[k];
+    __syncthreads();
+    double x[K], y[K];
+    for (int k = 0; k < K; ++k) { x[k] = in[threadIdx.x + k]; y[k] = in[threadIdx.x + 8 + k]; }
+    for (int it = 0; it < iters; ++it) {
+        const double *t = tab + base + (it & 7) * 64;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) x[k] = fma(y[(k + u) % K], t[u * (K / NS) + k / NS], x[k]);
+    }
+    double s = 0; for (int k = 0; k < K; ++k) s += x[k];
+    if (s == 123.456) out[threadIdx.x] = s;
+}
+
 template <class F> double bench(const char *name, F launch, int grid, int iters) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     double best = 1e30;
@@ -91,7 +125,7 @@ int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     const int iters = 4096;
     double *out, *in; cudaMalloc(&out, 1 << 20); cudaMalloc(&in, 1 << 20); cudaMemset(in, 0, 1 << 20);
-    for (int occ : {2, 4, 8}) {
+    for (int occ : {2, 8}) {
         const int grid = p.multiProcessorCount * occ;
         printf("--- %d blocks of 256 threads per SM (%d warps/SM)\n", occ, occ * 8);
         bench("a: reg x const x const", [&] { k_const<<<grid, 256>>>(out, iters, 0.999999, 1e-9); }, grid, iters);
@@ -99,6 +133,10 @@ int main() {
         bench("c: shared multiplicand (rank-1 pattern)", [&] { k_shared_g<<<grid, 256>>>(out, iters, in); }, grid, iters);
         bench("d: one source from __constant__[uniform idx]", [&] { k_cidx<<<grid, 256>>>(out, iters, in, 0); }, grid, iters);
         bench("e: one source from shared memory (broadcast)", [&] { k_smem<<<grid, 256>>>(out, iters, in, 0); }, grid, iters);
+        bench("f4: __constant__ operand shared by 4 DFMAs", [&] { k_cshare<4><<<grid, 256>>>(out, iters, in, 0); }, grid, iters);
+        bench("f8: __constant__ operand shared by 8 DFMAs", [&] { k_cshare<8><<<grid, 256>>>(out, iters, in, 0); }, grid, iters);
+        bench("g4: shared-memory operand shared by 4 DFMAs", [&] { k_sshare<4><<<grid, 256>>>(out, iters, in, 0); }, grid, iters);
+        bench("g8: shared-memory operand shared by 8 DFMAs", [&] { k_sshare<8><<<grid, 256>>>(out, iters, in, 0); }, grid, iters);
     }
     return 0;
 }
