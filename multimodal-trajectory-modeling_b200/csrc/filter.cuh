@@ -115,7 +115,6 @@ struct FilterState {
     double mant;               // running product of pivots, mantissa part (sign kept)
     int expo;                  // ... and its binary exponent
     int k;                     // number of present scalars
-    int bad;                   // MTM_STATUS_* bits
 };
 
 // element (i, j) of a symmetric matrix stored in its upper triangle
@@ -140,7 +139,6 @@ __device__ __forceinline__ void filter_init(const DM &dm, FilterState<DM> &f, co
     f.mant = 1.0;
     f.expo = 0;
     f.k = 0;
-    f.bad = 0;
 }
 
 // (mu, P) <- (mu A, A' P A + Gamma)     [SSM:62-64 for P, :312-314 for mu]
@@ -213,8 +211,6 @@ __device__ __forceinline__ void filter_condition_z(const DM &dm, FilterState<DM>
             const double y = zt[j];
             const bool obs = finite_bits(y) && ((finmask >> j) & 1u);
             const double s = f.P[j][j];
-            f.bad |= (obs && !finite_bits(s)) ? MTM_STATUS_NONFINITE : 0;
-            f.bad |= (obs && s == 0.0) ? MTM_STATUS_SINGULAR : 0;
             const double r = obs ? fast_rcp(s) : 0.0;
             const double v = obs ? (y - f.mu[j]) : 0.0;
             f.q = fma(v * v, r, f.q);
@@ -248,9 +244,11 @@ __device__ __forceinline__ void filter_condition_z(const DM &dm, FilterState<DM>
 }
 
 // predictive of x_t and conditioning on its present coordinates   [SSM:161-166, 217-222, 337-339]
+// LAST = true (final time step): the posterior of z_t is never used again, so the updates of
+// (mu, P) are skipped; pivots, innovations and the x-block updates are unchanged.
 template <class DM, class PV>
 __device__ __forceinline__ void filter_condition_x(const DM &dm, FilterState<DM> &f, const PV &p,
-                                                   const double (&xt)[DM::LM], uint32_t finmask) {
+                                                   const double (&xt)[DM::LM], uint32_t finmask, const bool LAST) {
     const int d = dm.d(), l = dm.l();
     double mux[DM::LM];
     double C[DM::DM][DM::LM];   // Cov(z_t, x_t | past) = P H
@@ -305,8 +303,6 @@ __device__ __forceinline__ void filter_condition_x(const DM &dm, FilterState<DM>
             const double y = xt[j];
             const bool obs = finite_bits(y) && ((finmask >> j) & 1u);
             const double s = Sx[j][j];
-            f.bad |= (obs && !finite_bits(s)) ? MTM_STATUS_NONFINITE : 0;
-            f.bad |= (obs && s == 0.0) ? MTM_STATUS_SINGULAR : 0;
             const double r = obs ? fast_rcp(s) : 0.0;
             const double v = obs ? (y - mux[j]) : 0.0;
             f.q = fma(v * v, r, f.q);
@@ -316,10 +312,12 @@ __device__ __forceinline__ void filter_condition_x(const DM &dm, FilterState<DM>
             for (int i = 0; i < DM::DM; ++i) {
                 if (i < d) {
                     const double g = C[i][j] * r;
-                    f.mu[i] = fma(g, v, f.mu[i]);
-                    MTM_UNROLL
-                    for (int a = i; a < DM::DM; ++a)
-                        if (a < d) f.P[i][a] = fma(-g, C[a][j], f.P[i][a]);
+                    if (!LAST) {
+                        f.mu[i] = fma(g, v, f.mu[i]);
+                        MTM_UNROLL
+                        for (int a = i; a < DM::DM; ++a)
+                            if (a < d) f.P[i][a] = fma(-g, C[a][j], f.P[i][a]);
+                    }
                     MTM_UNROLL
                     for (int b = j + 1; b < DM::LM; ++b)
                         if (b < l) C[i][b] = fma(-g, Sx[j][b], C[i][b]);
@@ -352,8 +350,15 @@ __device__ __forceinline__ void filter_rescale(FilterState<DM> &f) {
 
 // -1/2 (k log 2 pi + log det) - 1/2 q.  A negative determinant gives NaN like the reference's
 // log((2 pi)^k det) (:771-772); no present coordinate gives -0.0.
+//
+// Failure flags are derived here instead of per pivot: a NaN/inf pivot makes the determinant or the
+// quadratic form non-finite (NONFINITE: the reference's det/solve raise on such a block); an exactly
+// zero pivot makes the determinant exactly zero (SINGULAR).  A finite negative determinant is NOT an
+// error (the reference returns NaN for it without raising).
 template <class DM>
-__device__ __forceinline__ double filter_finish(const FilterState<DM> &f) {
+__device__ __forceinline__ double filter_finish(const FilterState<DM> &f, int &bad) {
+    bad |= (!finite_bits(f.mant) || !finite_bits(f.q)) ? MTM_STATUS_NONFINITE : 0;
+    bad |= (f.mant == 0.0) ? MTM_STATUS_SINGULAR : 0;
     const double logdet = fma((double)f.expo, 0.6931471805599453094, log(f.mant));
     return -0.5 * fma((double)f.k, 1.8378770664093454836, logdet) - 0.5 * f.q;
 }
@@ -391,21 +396,21 @@ __device__ __forceinline__ double filter_eval(const DM &dm, const double *__rest
     for (int t = 0; t < T0; ++t) {
         // software pipeline: issue the loads of step t+1 before the arithmetic of step t
         double zn[DM::DM], xn[DM::LM];
-        const int tn = (t + 1 < T0) ? t + 1 : t;
-        if (HAS_Z) load_row<DM::DM>(z_i + tn * zs, zn, dm.d(), DM::kStatic);
-        load_row<DM::LM>(x_i + tn * xs, xn, dm.l(), DM::kStatic);
+        const bool last = (t + 1 == T0);  // warp-uniform
+        const int tn = last ? t : t + 1;
+        if (HAS_Z) load_row<DM::DM>(z_i + (int64_t)tn * zs, zn, dm.d(), DM::kStatic);
+        load_row<DM::LM>(x_i + (int64_t)tn * xs, xn, dm.l(), DM::kStatic);
         const uint32_t fm = fin[t];
         if (t > 0) filter_propagate(dm, f, p);
         if (HAS_Z) filter_condition_z(dm, f, zt, fm & 0xffffu);
-        filter_condition_x(dm, f, p, xt, fm >> 16);
+        filter_condition_x(dm, f, p, xt, fm >> 16, last);
         filter_rescale(f);
         MTM_UNROLL
         for (int k = 0; k < DM::DM; ++k) zt[k] = zn[k];
         MTM_UNROLL
         for (int k = 0; k < DM::LM; ++k) xt[k] = xn[k];
     }
-    bad |= f.bad;
-    return filter_finish(f);
+    return filter_finish(f, bad);
 }
 
 // finiteness masks of the unconditional stacked mean [m A^t | m A^t H] for one cluster; run by one
