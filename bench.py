@@ -308,9 +308,13 @@ def main():
     def m_step():
         C.check(lib.mtm_mstep(h, vp(assign), cfg["n_c"], 0.0, vp(params), None), h)
 
+    # one EM iteration = mtm_em_step: phase 1 = E-step kernel with the M-step statistics fused into its
+    # epilogue + the two small reduction kernels (+ the all-reduce when N > 1); phase 2 = parameter solve
     def e_step():
-        C.check(lib.mtm_estep(h, ctypes.byref(st), vp(params), cfg["n_c"], args.T, vp(assign), 1, None, None, None,
-                              None), h)
+        C.check(lib.mtm_em_step(h, cfg["n_c"], 0.0, vp(assign), vp(params), 1, None), h)
+
+    def m_finish():
+        C.check(lib.mtm_em_step(h, cfg["n_c"], 0.0, vp(assign), vp(params), 2, None), h)
 
     def barrier():
         if world > 1:
@@ -320,7 +324,7 @@ def main():
     m_step()  # parameters of the initial assignment (train()'s first M-step)
     for _ in range(args.warmup):
         e_step()
-        m_step()
+        m_finish()
     barrier()
     fp64_peak = eng.fp64_peak(10)  # TFLOP/s, own DFMA micro-kernel (MEASURED_PEAKS.json has no fp64 entry)
     barrier()
@@ -336,7 +340,7 @@ def main():
             ev[k][0].record()
             e_step()
             ev[k][1].record()
-            m_step()
+            m_finish()
             ev[k][2].record()
         t_end.record()
         barrier()
@@ -366,15 +370,16 @@ def main():
     bpt = bytes_per_traj(args.T, args.d, args.l)
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak, "traffic": None,
-                "kernel": "estep_kernel<4,4,true>", "kernel_ms": ms_e,
+                "kernel": "estep_kernel<4,4,HAS_Z,CONSTP,FUSE> (E-step + fused M-step statistics; the timed span also "
+                          "holds the two ~10 us reduction kernels and, for N > 1, the all-reduce)",
+                "kernel_ms": ms_e,
                 "flops_per_eval": f_eval, "evals_per_launch": evals_launch,
                 "peak_source": "measured here: mtm_fp64_peak DFMA micro-kernel, best of 10 (nominal 37.2)",
                 "achieved_survey_formula": f_survey * evals_launch / (ms_e * 1e-3) * 1e-12,
                 "hbm": {"achieved": bpt * n_loc / (ms_e * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bpt * n_loc / (ms_e * 1e-3) * 1e-9 / hbm_peak, "bytes_per_trajectory": bpt,
                         "peak_source": hbm_src},
-                "mstep_ms": ms_m,
-                "mstep_hbm_gbs": bpt * n_loc / (ms_m * 1e-3) * 1e-9}
+                "finalize_ms": ms_m}
 
     # ---- parity gate on a prefix, against the CPU oracle ----
     parity = None
@@ -407,7 +412,7 @@ def main():
             z.copy_(zh, non_blocking=True)  # H2D of this step's inputs from pinned memory
             x.copy_(xh, non_blocking=True)
             e_step()
-            m_step()
+            m_finish()
             ah.copy_(assign, non_blocking=True)  # D2H of the step's result: labels + parameters
             ph.copy_(params, non_blocking=True)
 

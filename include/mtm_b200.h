@@ -146,6 +146,15 @@ int mtm_finalize(mtm_handle *h, const double *stats_dev, int n_c, int d, int l, 
 int mtm_mstep(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, double *params_dev,
               mtm_estep_info *info);
 
+/* ---- one EM iteration ------------------------------------------------------------------------------
+ * The reference's `E_step(); M_step()` pair (MMM:1341, 1357) without the convergence logic: E-step under
+ * params_dev (new labels into assign_dev, switch count), then M-step of the new labels into params_dev.
+ * The statistics are accumulated inside the E-step kernel (one pass over the data).  phases: bit 0 = the
+ * E-step + statistics + reduction (+ all-reduce) part, bit 1 = the parameter solve; 3 = both (the split
+ * only exists so that a benchmark can time the dominant kernel on its own).  Synchronises if info != NULL. */
+int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, double *params_dev, int phases,
+                mtm_estep_info *info);
+
 /* ---- EM fit --------------------------------------------------------------------------------------
  * train (MMM:1310-1366) on the resident set, loop resident on the device:
  *   guard -> M -> { E ; stop if 0 switches ; guard ; M } for at most n_steps E-steps.

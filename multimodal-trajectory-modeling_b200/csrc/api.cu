@@ -140,9 +140,13 @@ int check_dims(mtm_handle *h, const mtm_data *dt, int n_c) {
     return 0;
 }
 
+bool can_fuse(const mtm_data *dt, int n_c) {
+    return dt->z_dev != nullptr && estep_smem(n_c, dt->T, dt->d, dt->l, true) <= 72 * 1024;
+}
+
 int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n_c, int T0, int32_t *assign,
                   int count_switches, double *ll, double *probs, double *prenorm, unsigned long long *counts,
-                  double *score_partials, int check_done, int *grid_out) {
+                  double *score_partials, int check_done, int *grid_out, bool fused = false) {
     EStepArgs a{};
     a.z = dt->z_dev;
     a.x = dt->x_dev;
@@ -162,9 +166,14 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
     a.counts = counts;
     a.score_partials = score_partials;
     a.check_done = check_done;
-    const int grid = estep_grid(dt->n, h->sm_count);
+    const int grid = estep_grid(dt->n, h->sm_count, fused);
     if (grid_out) *grid_out = grid;
-    const size_t smem = estep_smem(n_c, a.T0, a.d, a.l);
+    if (fused) {
+        const size_t n_vals = (size_t)n_c * stats_stride(dt->d, dt->l);
+        if (int rc = ensure(h, h->d_partials, h->partials_cap, 2 * n_vals * ((size_t)grid + kReduceSlices))) return rc;
+        a.stats_partials = h->d_partials;
+    }
+    const size_t smem = estep_smem(n_c, a.T0, a.d, a.l, fused);
     if (smem > 200 * 1024) return fail(h, -1, "E-step shared memory %zu B too large (n_c * T0 too big)", smem);
     MTM_CUDA(h, launch_estep(a, grid, smem, h->stream));
     h->launches += 1;
@@ -178,19 +187,29 @@ int allreduce_stats(mtm_handle *h, double *buf, size_t count) {
     return 0;
 }
 
-// statistics of the resident set under `assign` -> h->d_statsbuf [n_c*sstride | n_switches | n_local],
+// block partials in h->d_partials (from `grid` blocks) -> h->d_statsbuf [n_c*sstride | n_switches | n_local],
 // all-reduced over the communicator
+int enqueue_stats_reduce(mtm_handle *h, int n_c, int grid, int check_done, int with_switches) {
+    const mtm_data &dt = h->data;
+    const int n_vals = n_c * stats_stride(dt.d, dt.l);
+    if (int rc = ensure(h, h->d_statsbuf, h->statsbuf_cap, (size_t)n_vals + 2)) return rc;
+    MTM_CUDA(h, launch_stats_reduce(h->d_partials, grid, n_vals, h->d_statsbuf,
+                                    h->d_partials + 2 * (size_t)grid * n_vals, h->d_ctrl, check_done,
+                                    with_switches ? &h->d_ctrl->n_switches : nullptr, (double)dt.n, h->stream));
+    h->launches += 2;
+    return allreduce_stats(h, h->d_statsbuf, (size_t)n_vals + 2);
+}
+
+// statistics of the resident set under `assign` (stand-alone kernel) + reduce + all-reduce
 int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done, int with_switches) {
     const mtm_data &dt = h->data;
-    const int sstride = stats_stride(dt.d, dt.l);
-    const int n_vals = n_c * sstride;
+    const size_t n_vals = (size_t)n_c * stats_stride(dt.d, dt.l);
     const int grid = stats_grid(dt.n, h->sm_count);
     const size_t smem = stats_smem(n_c, dt.d, dt.l);
     if (smem > 220 * 1024)
         return fail(h, -1, "statistics kernel needs %zu B of shared memory (n_c=%d, d=%d, l=%d): too large", smem, n_c,
                     dt.d, dt.l);
-    if (int rc = ensure(h, h->d_partials, h->partials_cap, (size_t)2 * grid * n_vals)) return rc;
-    if (int rc = ensure(h, h->d_statsbuf, h->statsbuf_cap, (size_t)n_vals + 2)) return rc;
+    if (int rc = ensure(h, h->d_partials, h->partials_cap, 2 * n_vals * ((size_t)grid + kReduceSlices))) return rc;
     StatsArgs s{};
     s.z = dt.z_dev;
     s.x = dt.x_dev;
@@ -204,10 +223,24 @@ int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done,
     s.ctrl = h->d_ctrl;
     s.check_done = check_done;
     MTM_CUDA(h, launch_stats(s, grid, h->stream));
-    MTM_CUDA(h, launch_stats_reduce(h->d_partials, grid, n_vals, h->d_statsbuf, h->d_ctrl, check_done,
-                                    with_switches ? &h->d_ctrl->n_switches : nullptr, (double)dt.n, h->stream));
-    h->launches += 2;
-    return allreduce_stats(h, h->d_statsbuf, (size_t)n_vals + 2);
+    h->launches += 1;
+    return enqueue_stats_reduce(h, n_c, grid, check_done, with_switches);
+}
+
+// one EM iteration's kernels: E-step (+ fused statistics when possible) -> reduce -> all-reduce
+int enqueue_e_and_stats(mtm_handle *h, int n_c, const double *params, int32_t *assign, int check_done) {
+    const mtm_data &dt = h->data;
+    if (can_fuse(&dt, n_c)) {
+        int grid = 0;
+        if (int rc = enqueue_estep(h, &dt, params, n_c, dt.T, assign, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   check_done, &grid, true))
+            return rc;
+        return enqueue_stats_reduce(h, n_c, grid, check_done, 1);
+    }
+    if (int rc = enqueue_estep(h, &dt, params, n_c, dt.T, assign, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
+                               check_done, nullptr, false))
+        return rc;
+    return enqueue_stats(h, assign, n_c, check_done, 1);
 }
 
 int enqueue_finalize(mtm_handle *h, int n_c, double alpha, double *params, int mode, int n_steps) {
@@ -358,7 +391,7 @@ int mtm_score(mtm_handle *h, const mtm_data *data, const double *params_dev, int
     const mtm_data *dt = data ? data : (h->has_data ? &h->data : nullptr);
     if (int rc = check_dims(h, dt, n_c)) return rc;
     DeviceGuard g(h->device);
-    const int grid = estep_grid(dt->n, h->sm_count);
+    const int grid = estep_grid(dt->n, h->sm_count, false);
     if (int rc = ensure(h, h->d_score, h->score_cap, (size_t)2 + 2 * grid)) return rc;
     MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
     if (int rc = enqueue_estep(h, dt, params_dev, n_c, dt->T, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
@@ -436,6 +469,30 @@ int mtm_mstep(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, d
     return 0;
 }
 
+int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, double *params_dev, int phases,
+                mtm_estep_info *info) {
+    if (!h) return -1;
+    if (!h->has_data) return fail(h, -1, "no resident data set (mtm_set_data)");
+    if (int rc = check_dims(h, &h->data, n_c)) return rc;
+    if (!assign_dev || !params_dev) return fail(h, -1, "NULL argument");
+    DeviceGuard g(h->device);
+    if (phases & 1) {
+        MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+        if (int rc = enqueue_e_and_stats(h, n_c, params_dev, assign_dev, 0)) return rc;
+    }
+    if (phases & 2) {
+        if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 0, 0)) return rc;
+    }
+    if (info) {
+        if (int rc = read_ctrl(h)) return rc;
+        info->n_switches = (int64_t)h->h_ctrl->n_switches;
+        info->min_count = h->h_ctrl->min_count;
+        info->status = h->h_ctrl->status;
+        info->reserved = 0;
+    }
+    return 0;
+}
+
 int mtm_em_fit(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assign_dev, double *params_dev,
                mtm_fit_info *info, int64_t *switches_host, int switches_cap) {
     if (!h) return -1;
@@ -464,10 +521,7 @@ int mtm_em_fit(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assig
     while (!h->h_ctrl->done && issued < n_steps) {
         const int nb = (n_steps - issued < batch) ? (n_steps - issued) : batch;
         for (int b = 0; b < nb; ++b) {
-            if (int rc = enqueue_estep(h, &dt, params_dev, n_c, dt.T, assign_dev, 1, nullptr, nullptr, nullptr, nullptr,
-                                       nullptr, 1, nullptr))
-                return rc;
-            if (int rc = enqueue_stats(h, assign_dev, n_c, 1, 1)) return rc;
+            if (int rc = enqueue_e_and_stats(h, n_c, params_dev, assign_dev, 1)) return rc;
             if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 1, n_steps)) return rc;
         }
         issued += nb;

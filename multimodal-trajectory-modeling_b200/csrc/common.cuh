@@ -38,6 +38,8 @@ struct EStepArgs {
     unsigned long long *counts;    // (n_c) cluster sizes after the E-step, nullable
     double *score_partials;        // nullable: (grid, 2) block sums of Q and LL terms
     int check_done;                // honour ctrl->done (EM loop) or not (stand-alone calls)
+    double *stats_partials;        // nullable: fused mode — the M-step statistics of the NEW labels are
+                                   // accumulated in the same pass: (grid, n_c, sstride, 2) block sums
 };
 
 struct StatsArgs {
@@ -65,16 +67,18 @@ struct FinalizeArgs {
 
 // launchers (one translation unit per kernel family so that nvcc can build them in parallel)
 cudaError_t launch_estep(const EStepArgs &a, int grid, size_t smem, cudaStream_t s);
-int estep_grid(int64_t n, int sm_count);
-size_t estep_smem(int n_c, int T0, int d, int l);
+int estep_grid(int64_t n, int sm_count, bool fused);
+size_t estep_smem(int n_c, int T0, int d, int l, bool fused);
 
 cudaError_t launch_stats(const StatsArgs &a, int grid, cudaStream_t s);
 int stats_grid(int64_t n, int sm_count);
 size_t stats_smem(int n_c, int d, int l);
-// out (n_vals + 2): reduced statistics, then [n_switches of the preceding E-step, local n]
-cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, const Ctrl *ctrl,
-                                int check_done, const unsigned long long *n_switches_src, double n_local,
-                                cudaStream_t s);
+// out (n_vals + 2): reduced statistics, then [n_switches of the preceding E-step, local n].
+// `scratch` holds kReduceSlices * n_vals * 2 doubles (two-stage fixed-order reduction).
+constexpr int kReduceSlices = 16;
+cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
+                                const Ctrl *ctrl, int check_done, const unsigned long long *n_switches_src,
+                                double n_local, cudaStream_t s);
 // tail (nullable) = the two trailing slots of the all-reduced statistics buffer
 cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStream_t s);
 cudaError_t launch_counts(const int32_t *assign, int64_t n, int n_c, unsigned long long *counts, cudaStream_t s);

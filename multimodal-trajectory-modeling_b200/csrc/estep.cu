@@ -16,6 +16,7 @@
 #include "common.cuh"
 #define MTM_DEFINE_CONST_PARAMS
 #include "filter.cuh"
+#include "stats_tile.cuh"
 
 namespace mtm {
 
@@ -45,7 +46,10 @@ struct PSel<false> {
     }
 };
 
-template <int D_, int L_, bool HAS_Z, bool CONSTP>
+// FUSE: the sufficient statistics of the M-step (stats_tile.cuh) are accumulated for the labels
+// this very pass assigns, while the tile's trajectories are still hot in L1/L2 and the FP64 work of
+// the other resident blocks hides the latency: one HBM pass per EM iteration instead of two.
+template <int D_, int L_, bool HAS_Z, bool CONSTP, bool FUSE>
 __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     using DM = Dims<D_, L_>;
     using PS = PSel<CONSTP>;
@@ -59,6 +63,11 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     double *s_pi = s_logpi + a.n_c;                                       // n_c
     uint32_t *s_fin = reinterpret_cast<uint32_t *>(s_pi + a.n_c);         // n_c * T0
     unsigned int *s_cnt = s_fin + a.n_c * a.T0;                           // n_c
+    StatsSmem ssm;
+    if (FUSE) {
+        const size_t eb = ((reinterpret_cast<unsigned char *>(s_cnt + a.n_c) - smem_raw) + 15) & ~size_t(15);
+        ssm.carve(smem_raw + eb, a.n_c, dm.d(), dm.l());
+    }
     __shared__ double s_red[2][kEThreads / 32];
     __shared__ unsigned int s_sw;
 
@@ -66,6 +75,8 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     if (!CONSTP)
         for (int k = tid; k < a.n_c * stride; k += kEThreads) s_par[k] = a.params[k];
     for (int k = tid; k < a.n_c; k += kEThreads) s_cnt[k] = 0;
+    if (FUSE)
+        for (int k = tid; k < 2 * a.n_c * stats_stride(dm.d(), dm.l()); k += kEThreads) ssm.acc[k] = 0.0;
     if (tid == 0) s_sw = 0;
     __syncthreads();
     for (int c = tid; c < a.n_c; c += kEThreads) {
@@ -130,6 +141,7 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
                 if ((tid & 31) == 0 && m) atomicAdd(&s_cnt[c], (unsigned int)__popc(m));
             }
         }
+        if (FUSE) stats_tile(dm, a.z, a.x, n, a.T, i, valid ? arg : -1, a.n_c, ssm);
     }
 
     // block epilogue: integer counters by atomics (exact, order-free), fp64 sums in a fixed order
@@ -166,6 +178,11 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     if (a.counts)
         for (int c = tid; c < a.n_c; c += kEThreads)
             if (s_cnt[c]) atomicAdd(&a.counts[c], (unsigned long long)s_cnt[c]);
+    if (FUSE) {
+        const int nv = 2 * a.n_c * stats_stride(dm.d(), dm.l());
+        double *out = a.stats_partials + (size_t)blockIdx.x * nv;
+        for (int k = tid; k < nv; k += kEThreads) out[k] = ssm.acc[k];
+    }
 }
 
 // fixed-order sum of the per-block (Q, LL) partials
@@ -192,21 +209,24 @@ __global__ void score_reduce_kernel(const double *__restrict__ partials, int gri
     }
 }
 
-size_t estep_smem(int n_c, int T0, int d, int l) {
-    return (size_t)n_c * param_stride(d, l) * 8 + (size_t)n_c * 16 + (size_t)n_c * T0 * 4 + (size_t)n_c * 4 + 16;
+size_t estep_smem(int n_c, int T0, int d, int l, bool fused) {
+    const size_t e = (size_t)n_c * param_stride(d, l) * 8 + (size_t)n_c * 16 + (size_t)n_c * T0 * 4 + (size_t)n_c * 4 + 32;
+    return e + (fused ? stats_smem_bytes(n_c, d, l) : 0);
 }
 
-int estep_grid(int64_t n, int sm_count) {
+int estep_grid(int64_t n, int sm_count, bool fused) {
     const int64_t tiles = (n + kEThreads - 1) / kEThreads;
-    // enough blocks for every SM to hold its resident set several times over, so that the static
-    // tile striding balances; never more blocks than tiles
-    const int64_t cap = (int64_t)sm_count * 32;
+    // Static tile striding (uniform cost per tile).  Plain E-step: enough blocks for every SM to hold
+    // its resident set several times over.  Fused: every block also carries n_c*106 double-double
+    // accumulators that a reduction has to read back, so fewer, longer-lived blocks (6 per SM; the
+    // imbalance of the last wave is then at most one tile in ~90 at 10 M trajectories).
+    const int64_t cap = (int64_t)sm_count * (fused ? 6 : 32);
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
-template <int D_, int L_, bool HAS_Z, bool CONSTP>
+template <int D_, int L_, bool HAS_Z, bool CONSTP, bool FUSE = false>
 static cudaError_t launch_one(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
-    auto k = estep_kernel<D_, L_, HAS_Z, CONSTP>;
+    auto k = estep_kernel<D_, L_, HAS_Z, CONSTP, FUSE>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -223,8 +243,10 @@ static cudaError_t launch_dl(const EStepArgs &a, int grid, size_t smem, cudaStre
         cudaError_t e = cudaMemcpyToSymbolAsync(c_par, a.params, n_par * sizeof(double), 0,
                                                 cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
+        if (a.stats_partials) return launch_one<D_, L_, true, true, true>(a, grid, smem, s);
         return a.z ? launch_one<D_, L_, true, true>(a, grid, smem, s) : launch_one<D_, L_, false, true>(a, grid, smem, s);
     }
+    if (a.stats_partials) return launch_one<D_, L_, true, false, true>(a, grid, smem, s);
     return a.z ? launch_one<D_, L_, true, false>(a, grid, smem, s) : launch_one<D_, L_, false, false>(a, grid, smem, s);
 }
 

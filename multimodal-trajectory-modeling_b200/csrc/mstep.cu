@@ -18,222 +18,65 @@
 // not grow with n.
 #include "common.cuh"
 #include "filter.cuh"
+#include "stats_tile.cuh"
 
 namespace mtm {
-
-// (hi, lo) += x, error-free (Knuth two-sum)
-__device__ __forceinline__ void dd_add(double &hi, double &lo, double x) {
-    const double t = hi + x;
-    const double bp = t - hi;
-    const double e = (hi - (t - bp)) + (x - bp);
-    hi = t;
-    lo += e;
-}
-
-template <int K>
-struct Moments {  // [count | sum v (K) | sum v v' upper (K(K+1)/2)]
-    static constexpr int F = 1 + K + K * (K + 1) / 2;
-};
-
-// acc += moments of v (all K components finite) else nothing
-template <int KM>
-__device__ __forceinline__ void add_moments(double *acc, const double (&v)[KM], int K, bool ok) {
-    acc[0] += ok ? 1.0 : 0.0;
-    double w[KM];
-    MTM_UNROLL
-    for (int a = 0; a < KM; ++a)
-        if (a < K) w[a] = ok ? v[a] : 0.0;
-    MTM_UNROLL
-    for (int a = 0; a < KM; ++a)
-        if (a < K) acc[1 + a] += w[a];
-    int o = 1 + K;
-    MTM_UNROLL
-    for (int a = 0; a < KM; ++a) {
-        if (a < K) {
-            MTM_UNROLL
-            for (int b = a; b < KM; ++b)
-                if (b < K) acc[o + (b - a)] = fma(w[a], w[b], acc[o + (b - a)]);
-            o += K - a;
-        }
-    }
-}
-
-template <int NM>
-__device__ __forceinline__ bool all_finite(const double (&v)[NM], int n) {
-    bool ok = true;
-    MTM_UNROLL
-    for (int a = 0; a < NM; ++a)
-        if (a < n) ok = ok && finite_bits(v[a]);
-    return ok;
-}
-
-// block-level reduce-by-cluster of per-trajectory features that sit in registers
-//   feat[f] (f < F) of thread tid -> s_feat[f * ST + tid]; task (c, f) sums the members of c.
-template <int FM>
-__device__ __forceinline__ void reduce_by_cluster(const double *feat, int F, double *s_feat, const int *s_list,
-                                                  const int *s_start, int n_c, double *s_acc, int sstride,
-                                                  int gofs) {
-    constexpr int ST = kSThreads + 1;
-    const int tid = threadIdx.x;
-    MTM_UNROLL
-    for (int f = 0; f < FM; ++f)
-        if (f < F) s_feat[f * ST + tid] = feat[f];
-    __syncthreads();
-    for (int task = tid; task < n_c * F; task += kSThreads) {
-        const int c = task / F, f = task - c * F;
-        const int b = s_start[c], e = s_start[c + 1];
-        if (e > b) {
-            const double *row = s_feat + f * ST;
-            double s0 = 0.0, s1 = 0.0;  // two interleaved chains in a fixed pattern
-            int r = b;
-            for (; r + 1 < e; r += 2) {
-                s0 += row[s_list[r]];
-                s1 += row[s_list[r + 1]];
-            }
-            if (r < e) s0 += row[s_list[r]];
-            double *acc = s_acc + 2 * ((size_t)c * sstride + gofs + f);
-            dd_add(acc[0], acc[1], s0 + s1);
-        }
-    }
-    __syncthreads();
-}
 
 template <int D_, int L_>
 __global__ void __launch_bounds__(kSThreads) stats_kernel(const StatsArgs a) {
     using DM = Dims<D_, L_>;
     const DM dm{a.d, a.l};
     if (a.check_done && a.ctrl->done) return;
-    const int d = dm.d(), l = dm.l();
-    constexpr int DMX = DM::DM, LMX = DM::LM;
-    constexpr int K1 = DMX, K2 = 2 * DMX, K3 = DMX + LMX;
-    constexpr int F1M = Moments<K1>::F, F2M = Moments<K2>::F, F3M = Moments<K3>::F;
-    const int F1 = 1 + d + d * (d + 1) / 2, F2 = 1 + 2 * d + d * (2 * d + 1);
-    const int F3 = 1 + (d + l) + (d + l) * (d + l + 1) / 2;
-    const int sstride = 1 + F1 + F2 + F3;
     const int n_c = a.n_c;
-
+    const int sstride = stats_stride(dm.d(), dm.l());
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_acc = reinterpret_cast<double *>(smem_raw);       // n_c * sstride * 2 (hi, lo)
-    const int FMAXRT = (F2 > F3 ? F2 : F3);
-    double *s_feat = s_acc + 2 * (size_t)n_c * sstride;          // FMAX * (kSThreads + 1)
-    int *s_list = reinterpret_cast<int *>(s_feat + (size_t)FMAXRT * (kSThreads + 1));  // kSThreads
-    int *s_start = s_list + kSThreads;                           // n_c + 1
-    int *s_wcnt = s_start + (n_c + 1);                           // warps * n_c
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kSThreads / 32;
-    for (int k = tid; k < 2 * n_c * sstride; k += kSThreads) s_acc[k] = 0.0;
+    StatsSmem sm;
+    sm.carve(smem_raw, n_c, dm.d(), dm.l());
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 2 * n_c * sstride; k += kSThreads) sm.acc[k] = 0.0;
     __syncthreads();
-
     const int64_t n = a.n;
     const int64_t n_tiles = (n + kSThreads - 1) / kSThreads;
-    const int64_t zs = n * d, xs = n * l;
-
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i_raw = tile * kSThreads + tid;
         const bool valid = i_raw < n;
         const int64_t i = valid ? i_raw : n - 1;
-        int label = valid ? a.assign[i] : -1;
-        if (label < 0 || label >= n_c) label = -1;
-
-        // ---- stable counting sort of the tile's labels -> member lists ----
-        int my_rank = 0;
-        for (int c = 0; c < n_c; ++c) {
-            const unsigned int m = __ballot_sync(0xffffffffu, label == c);
-            if (lane == 0) s_wcnt[warp * n_c + c] = __popc(m);
-            if (label == c) my_rank = __popc(m & ((1u << lane) - 1u));
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int run = 0;
-            for (int c = 0; c < n_c; ++c) {
-                s_start[c] = run;
-                for (int w = 0; w < NW; ++w) run += s_wcnt[w * n_c + c];
-            }
-            s_start[n_c] = run;
-        }
-        __syncthreads();
-        if (label >= 0) {
-            int off = s_start[label];
-            for (int w = 0; w < warp; ++w) off += s_wcnt[w * n_c + label];
-            s_list[off + my_rank] = tid;
-        }
-        // cluster sizes: exact integers, carried as doubles (< 2^53)
-        for (int c = tid; c < n_c; c += kSThreads) {
-            double *acc = s_acc + 2 * ((size_t)c * sstride);
-            dd_add(acc[0], acc[1], (double)(s_start[c + 1] - s_start[c]));
-        }
-
-        const double *z_i = a.z + i * d;
-        const double *x_i = a.x + i * l;
-
-        // ---- pass 1: initial-state and transition moments ----
-        {
-            double f1[F1M], f2[F2M];
-            MTM_UNROLL
-            for (int k = 0; k < F1M; ++k) f1[k] = 0.0;
-            MTM_UNROLL
-            for (int k = 0; k < F2M; ++k) f2[k] = 0.0;
-            double zc[DMX], zn[DMX];
-            load_row<DMX>(z_i, zc, d, DM::kStatic);
-            bool okc = all_finite<DMX>(zc, d);
-            add_moments<K1>(f1, zc, d, okc && label >= 0);
-            for (int t = 0; t + 1 < a.T; ++t) {
-                load_row<DMX>(z_i + (int64_t)(t + 1) * zs, zn, d, DM::kStatic);
-                const bool okn = all_finite<DMX>(zn, d);
-                double u[K2];
-                MTM_UNROLL
-                for (int k = 0; k < DMX; ++k)
-                    if (k < d) {
-                        u[k] = zc[k];
-                        u[d + k] = zn[k];
-                    }
-                add_moments<K2>(f2, u, 2 * d, okc && okn && label >= 0);
-                MTM_UNROLL
-                for (int k = 0; k < DMX; ++k) zc[k] = zn[k];
-                okc = okn;
-            }
-            reduce_by_cluster<F1M>(f1, F1, s_feat, s_list, s_start, n_c, s_acc, sstride, 1);
-            reduce_by_cluster<F2M>(f2, F2, s_feat, s_list, s_start, n_c, s_acc, sstride, 1 + F1);
-        }
-        // ---- pass 2: measurement moments ----
-        {
-            double f3[F3M];
-            MTM_UNROLL
-            for (int k = 0; k < F3M; ++k) f3[k] = 0.0;
-            for (int t = 0; t < a.T; ++t) {
-                double zc[DMX], xc[LMX];
-                load_row<DMX>(z_i + (int64_t)t * zs, zc, d, DM::kStatic);
-                load_row<LMX>(x_i + (int64_t)t * xs, xc, l, DM::kStatic);
-                const bool ok = all_finite<DMX>(zc, d) && all_finite<LMX>(xc, l);
-                double w[K3];
-                MTM_UNROLL
-                for (int k = 0; k < DMX; ++k)
-                    if (k < d) w[k] = zc[k];
-                MTM_UNROLL
-                for (int k = 0; k < LMX; ++k)
-                    if (k < l) w[d + k] = xc[k];
-                add_moments<K3>(f3, w, d + l, ok && label >= 0);
-            }
-            reduce_by_cluster<F3M>(f3, F3, s_feat, s_list, s_start, n_c, s_acc, sstride, 1 + F1 + F2);
-        }
+        stats_tile(dm, a.z, a.x, n, a.T, i, valid ? a.assign[i] : -1, n_c, sm);
     }
     __syncthreads();
     double *out = a.partials + 2 * (size_t)blockIdx.x * n_c * sstride;
-    for (int k = tid; k < 2 * n_c * sstride; k += kSThreads) out[k] = s_acc[k];
+    for (int k = tid; k < 2 * n_c * sstride; k += kSThreads) out[k] = sm.acc[k];
 }
 
-// out[v] = sum over blocks (in block order) of the (hi, lo) partials; tail slots:
-//   out[n_vals] = n_switches of the preceding E-step (exact integer as double), out[n_vals+1] = local n
-__global__ void stats_reduce_kernel(const double *__restrict__ partials, int grid, int n_vals, double *out,
-                                    const Ctrl *ctrl, int check_done, const unsigned long long *n_switches_src,
-                                    double n_local) {
+// Two-stage fixed-order reduction of the per-block (hi, lo) partials.
+//  stage 1: slice s (blockIdx.y) adds blocks s, s + S, s + 2S, ... in that order  -> scratch[s][v]
+//  stage 2: thread v adds the S slices in order                                  -> out[v]
+// tail slots: out[n_vals] = n_switches of the preceding E-step (exact integer as double),
+//             out[n_vals+1] = local n
+__global__ void stats_reduce1_kernel(const double *__restrict__ partials, int grid, int n_vals, double *scratch,
+                                     const Ctrl *ctrl, int check_done) {
+    if (check_done && ctrl->done) return;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y, S = gridDim.y;
+    if (v >= n_vals) return;
+    double hi = 0.0, lo = 0.0;
+    for (int b = s; b < grid; b += S) {
+        const double2 p = *reinterpret_cast<const double2 *>(partials + 2 * ((size_t)b * n_vals + v));
+        dd_add(hi, lo, p.x);
+        lo += p.y;
+    }
+    *reinterpret_cast<double2 *>(scratch + 2 * ((size_t)s * n_vals + v)) = make_double2(hi, lo);
+}
+
+__global__ void stats_reduce2_kernel(const double *__restrict__ scratch, int S, int n_vals, double *out,
+                                     const Ctrl *ctrl, int check_done, const unsigned long long *n_switches_src,
+                                     double n_local) {
     if (check_done && ctrl->done) return;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v < n_vals) {
         double hi = 0.0, lo = 0.0;
-        for (int b = 0; b < grid; ++b) {
-            const double2 p = *reinterpret_cast<const double2 *>(partials + 2 * ((size_t)b * n_vals + v));
+        for (int s = 0; s < S; ++s) {
+            const double2 p = *reinterpret_cast<const double2 *>(scratch + 2 * ((size_t)s * n_vals + v));
             dd_add(hi, lo, p.x);
             lo += p.y;
         }
@@ -459,12 +302,7 @@ __global__ void counts_kernel(const int32_t *__restrict__ assign, int64_t n, int
         if (s[c]) atomicAdd(&counts[c], (unsigned long long)s[c]);
 }
 
-size_t stats_smem(int n_c, int d, int l) {
-    const int F2 = 1 + 2 * d + d * (2 * d + 1), F3 = 1 + (d + l) + (d + l) * (d + l + 1) / 2;
-    const int FMAX = F2 > F3 ? F2 : F3;
-    return (size_t)2 * n_c * stats_stride(d, l) * 8 + (size_t)FMAX * (kSThreads + 1) * 8 + kSThreads * 4 +
-           (size_t)(n_c + 1) * 4 + (size_t)(kSThreads / 32) * n_c * 4 + 16;
-}
+size_t stats_smem(int n_c, int d, int l) { return stats_smem_bytes(n_c, d, l); }
 
 int stats_grid(int64_t n, int sm_count) {
     const int64_t tiles = (n + kSThreads - 1) / kSThreads;
@@ -498,12 +336,14 @@ cudaError_t launch_stats(const StatsArgs &a, int grid, cudaStream_t s) {
     return launch_stats_dl<0, 0>(a, grid, s);
 }
 
-cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, const Ctrl *ctrl,
-                                int check_done, const unsigned long long *n_switches_src, double n_local,
-                                cudaStream_t s) {
+cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
+                                const Ctrl *ctrl, int check_done, const unsigned long long *n_switches_src,
+                                double n_local, cudaStream_t s) {
     const int threads = 128;
-    stats_reduce_kernel<<<(n_vals + threads - 1) / threads, threads, 0, s>>>(partials, grid, n_vals, out, ctrl,
-                                                                               check_done, n_switches_src, n_local);
+    const int S = grid >= 4 * kReduceSlices ? kReduceSlices : 1;
+    const dim3 g1((n_vals + threads - 1) / threads, S);
+    stats_reduce1_kernel<<<g1, threads, 0, s>>>(partials, grid, n_vals, scratch, ctrl, check_done);
+    stats_reduce2_kernel<<<g1.x, threads, 0, s>>>(scratch, S, n_vals, out, ctrl, check_done, n_switches_src, n_local);
     return cudaGetLastError();
 }
 

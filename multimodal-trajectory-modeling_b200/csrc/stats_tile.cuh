@@ -1,0 +1,214 @@
+// Sufficient statistics of one 128-trajectory tile, reduced by cluster into the block's shared-memory
+// accumulators.  Shared by the stand-alone statistics kernel (mstep.cu) and the fused E-step
+// (estep.cu): see the header comment of mstep.cu for the method.
+#pragma once
+#include "common.cuh"
+#include "filter.cuh"
+
+namespace mtm {
+
+// (hi, lo) += x, error-free (Knuth two-sum)
+__device__ __forceinline__ void dd_add(double &hi, double &lo, double x) {
+    const double t = hi + x;
+    const double bp = t - hi;
+    const double e = (hi - (t - bp)) + (x - bp);
+    hi = t;
+    lo += e;
+}
+
+template <int K>
+struct Moments {  // [count | sum v (K) | sum v v' upper (K(K+1)/2)]
+    static constexpr int F = 1 + K + K * (K + 1) / 2;
+};
+
+// acc += moments of v (all K components finite) else nothing
+template <int KM>
+__device__ __forceinline__ void add_moments(double *acc, const double (&v)[KM], int K, bool ok) {
+    acc[0] += ok ? 1.0 : 0.0;
+    double w[KM];
+    MTM_UNROLL
+    for (int a = 0; a < KM; ++a)
+        if (a < K) w[a] = ok ? v[a] : 0.0;
+    MTM_UNROLL
+    for (int a = 0; a < KM; ++a)
+        if (a < K) acc[1 + a] += w[a];
+    int o = 1 + K;
+    MTM_UNROLL
+    for (int a = 0; a < KM; ++a) {
+        if (a < K) {
+            MTM_UNROLL
+            for (int b = a; b < KM; ++b)
+                if (b < K) acc[o + (b - a)] = fma(w[a], w[b], acc[o + (b - a)]);
+            o += K - a;
+        }
+    }
+}
+
+template <int NM>
+__device__ __forceinline__ bool all_finite(const double (&v)[NM], int n) {
+    bool ok = true;
+    MTM_UNROLL
+    for (int a = 0; a < NM; ++a)
+        if (a < n) ok = ok && finite_bits(v[a]);
+    return ok;
+}
+
+// block-level reduce-by-cluster of per-trajectory features that sit in registers
+//   feat[f] (f < F) of thread tid -> s_feat[f * ST + tid]; task (c, f) sums the members of c.
+template <int FM>
+__device__ __forceinline__ void reduce_by_cluster(const double *feat, int F, double *s_feat, const int *s_list,
+                                                  const int *s_start, int n_c, double *s_acc, int sstride,
+                                                  int gofs) {
+    constexpr int ST = kSThreads + 1;
+    const int tid = threadIdx.x;
+    MTM_UNROLL
+    for (int f = 0; f < FM; ++f)
+        if (f < F) s_feat[f * ST + tid] = feat[f];
+    __syncthreads();
+    for (int task = tid; task < n_c * F; task += kSThreads) {
+        const int c = task / F, f = task - c * F;
+        const int b = s_start[c], e = s_start[c + 1];
+        if (e > b) {
+            const double *row = s_feat + f * ST;
+            double s0 = 0.0, s1 = 0.0;  // two interleaved chains in a fixed pattern
+            int r = b;
+            for (; r + 1 < e; r += 2) {
+                s0 += row[s_list[r]];
+                s1 += row[s_list[r + 1]];
+            }
+            if (r < e) s0 += row[s_list[r]];
+            double *acc = s_acc + 2 * ((size_t)c * sstride + gofs + f);
+            dd_add(acc[0], acc[1], s0 + s1);
+        }
+    }
+    __syncthreads();
+}
+
+// shared-memory carve-up of the statistics part of a block
+struct StatsSmem {
+    double *acc;   // n_c * sstride * 2 (hi, lo)
+    double *feat;  // FMAX * (kSThreads + 1)
+    int *list;     // kSThreads
+    int *start;    // n_c + 1
+    int *wcnt;     // warps * n_c
+    __device__ __forceinline__ void carve(unsigned char *base, int n_c, int d, int l) {
+        const int F2 = 1 + 2 * d + d * (2 * d + 1), F3 = 1 + (d + l) + (d + l) * (d + l + 1) / 2;
+        const int FMAX = F2 > F3 ? F2 : F3;
+        acc = reinterpret_cast<double *>(base);
+        feat = acc + 2 * (size_t)n_c * stats_stride(d, l);
+        list = reinterpret_cast<int *>(feat + (size_t)FMAX * (kSThreads + 1));
+        start = list + kSThreads;
+        wcnt = start + (n_c + 1);
+    }
+};
+
+__host__ __device__ inline size_t stats_smem_bytes(int n_c, int d, int l) {
+    const int F2 = 1 + 2 * d + d * (2 * d + 1), F3 = 1 + (d + l) + (d + l) * (d + l + 1) / 2;
+    const int FMAX = F2 > F3 ? F2 : F3;
+    return (size_t)2 * n_c * stats_stride(d, l) * 8 + (size_t)FMAX * (kSThreads + 1) * 8 + kSThreads * 4 +
+           (size_t)(n_c + 1) * 4 + (size_t)(kSThreads / 32) * n_c * 4 + 16;
+}
+
+// One tile.  Every thread of the block must call it (it synchronises); `label` is the cluster of
+// trajectory i (any value outside [0, n_c) = not counted), `i` a valid (clamped) trajectory index.
+template <class DM>
+__device__ __forceinline__ void stats_tile(const DM &dm, const double *__restrict__ z, const double *__restrict__ x,
+                                           int64_t n, int T, int64_t i, int label, int n_c, const StatsSmem &sm) {
+    const int d = dm.d(), l = dm.l();
+    constexpr int DMX = DM::DM, LMX = DM::LM;
+    constexpr int K1 = DMX, K2 = 2 * DMX, K3 = DMX + LMX;
+    constexpr int F1M = Moments<K1>::F, F2M = Moments<K2>::F, F3M = Moments<K3>::F;
+    const int F1 = 1 + d + d * (d + 1) / 2, F2 = 1 + 2 * d + d * (2 * d + 1);
+    const int F3 = 1 + (d + l) + (d + l) * (d + l + 1) / 2;
+    const int sstride = 1 + F1 + F2 + F3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSThreads / 32;
+    const int64_t zs = n * d, xs = n * l;
+    double *s_acc = sm.acc, *s_feat = sm.feat;
+    int *s_list = sm.list, *s_start = sm.start, *s_wcnt = sm.wcnt;
+    if (label < 0 || label >= n_c) label = -1;
+
+    // ---- stable counting sort of the tile's labels -> member lists ----
+    int my_rank = 0;
+    for (int c = 0; c < n_c; ++c) {
+        const unsigned int m = __ballot_sync(0xffffffffu, label == c);
+        if (lane == 0) s_wcnt[warp * n_c + c] = __popc(m);
+        if (label == c) my_rank = __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int c = 0; c < n_c; ++c) {
+            s_start[c] = run;
+            for (int w = 0; w < NW; ++w) run += s_wcnt[w * n_c + c];
+        }
+        s_start[n_c] = run;
+    }
+    __syncthreads();
+    if (label >= 0) {
+        int off = s_start[label];
+        for (int w = 0; w < warp; ++w) off += s_wcnt[w * n_c + label];
+        s_list[off + my_rank] = tid;
+    }
+    // cluster sizes: exact integers, carried as doubles (< 2^53)
+    for (int c = tid; c < n_c; c += kSThreads) {
+        double *acc = s_acc + 2 * ((size_t)c * sstride);
+        dd_add(acc[0], acc[1], (double)(s_start[c + 1] - s_start[c]));
+    }
+
+    const double *z_i = z + i * d;
+    const double *x_i = x + i * l;
+
+    // ---- pass 1: initial-state and transition moments ----
+    {
+        double f1[F1M], f2[F2M];
+        MTM_UNROLL
+        for (int k = 0; k < F1M; ++k) f1[k] = 0.0;
+        MTM_UNROLL
+        for (int k = 0; k < F2M; ++k) f2[k] = 0.0;
+        double zc[DMX], zn[DMX];
+        load_row<DMX>(z_i, zc, d, DM::kStatic);
+        bool okc = all_finite<DMX>(zc, d);
+        add_moments<K1>(f1, zc, d, okc && label >= 0);
+        for (int t = 0; t + 1 < T; ++t) {
+            load_row<DMX>(z_i + (int64_t)(t + 1) * zs, zn, d, DM::kStatic);
+            const bool okn = all_finite<DMX>(zn, d);
+            double u[K2];
+            MTM_UNROLL
+            for (int k = 0; k < DMX; ++k)
+                if (k < d) {
+                    u[k] = zc[k];
+                    u[d + k] = zn[k];
+                }
+            add_moments<K2>(f2, u, 2 * d, okc && okn && label >= 0);
+            MTM_UNROLL
+            for (int k = 0; k < DMX; ++k) zc[k] = zn[k];
+            okc = okn;
+        }
+        reduce_by_cluster<F1M>(f1, F1, s_feat, s_list, s_start, n_c, s_acc, sstride, 1);
+        reduce_by_cluster<F2M>(f2, F2, s_feat, s_list, s_start, n_c, s_acc, sstride, 1 + F1);
+    }
+    // ---- pass 2: measurement moments ----
+    {
+        double f3[F3M];
+        MTM_UNROLL
+        for (int k = 0; k < F3M; ++k) f3[k] = 0.0;
+        for (int t = 0; t < T; ++t) {
+            double zc[DMX], xc[LMX];
+            load_row<DMX>(z_i + (int64_t)t * zs, zc, d, DM::kStatic);
+            load_row<LMX>(x_i + (int64_t)t * xs, xc, l, DM::kStatic);
+            const bool ok = all_finite<DMX>(zc, d) && all_finite<LMX>(xc, l);
+            double w[K3];
+            MTM_UNROLL
+            for (int k = 0; k < DMX; ++k)
+                if (k < d) w[k] = zc[k];
+            MTM_UNROLL
+            for (int k = 0; k < LMX; ++k)
+                if (k < l) w[d + k] = xc[k];
+            add_moments<K3>(f3, w, d + l, ok && label >= 0);
+        }
+        reduce_by_cluster<F3M>(f3, F3, s_feat, s_list, s_start, n_c, s_acc, sstride, 1 + F1 + F2);
+    }
+}
+
+}  // namespace mtm
