@@ -166,6 +166,24 @@ int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, doubl
 int mtm_em_fit(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assign_dev,
                double *params_dev, mtm_fit_info *info, int64_t *switches_host, int switches_cap);
 
+/* ---- batched restarts (kernel 4) -------------------------------------------------------------------
+ * n_restarts independent EM fits of the resident set with the same n_c, advanced in lock-step: every
+ * kernel of an iteration serves all still-running fits at once (one grid row per fit), so a thousand
+ * small fits cost a few launches per iteration instead of a few thousand.  This is the loop body of
+ * train_with_multiple_random_starts (MMM:1447-1464) and of model-selection.py:45-54 for one n_c; the
+ * caller runs it once per n_c of a sweep.
+ *   assign_dev   (n_restarts, n) int32 in/out: initial assignments in (e.g. rng.integers for seeds 100+i,
+ *                MMM:166-168), final assignments out
+ *   params_dev   (n_restarts, n_c, param_stride) out
+ *   info_host    [n_restarts]: exit code, E/M-step counts, status of every fit (same rules as mtm_em_fit)
+ *   scores_host  (n_restarts, 2) nullable: Q and LL of every final model (MMM:579-666), one launch
+ *   score_status_host [n_restarts] nullable: MTM_STATUS_* bits raised while scoring
+ *   switches_host (n_restarts, switches_cap) nullable: switch counts per E-step
+ * With a communicator attached all ranks call it on their shards. */
+int mtm_sweep_fit(mtm_handle *h, int n_c, int n_restarts, double alpha, int n_steps, int32_t *assign_dev,
+                  double *params_dev, mtm_fit_info *info_host, double *scores_host, int32_t *score_status_host,
+                  int64_t *switches_host, int switches_cap);
+
 /* ---- data-parallel sharding (one process per GPU) ----------------------------------------------
  * The library opens the NCCL that is already loaded in the process (libnccl.so.2).  Rank 0 obtains
  * an id with mtm_comm_unique_id and distributes the 128 bytes by any means (the Python host uses

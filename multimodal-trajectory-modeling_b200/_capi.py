@@ -63,6 +63,8 @@ SIGNATURES = {
     "mtm_mstep": (_i, [_vp, _vp, _i, _d, _vp, ctypes.POINTER(EStepInfo)]),
     "mtm_em_step": (_i, [_vp, _i, _d, _vp, _vp, _i, ctypes.POINTER(EStepInfo)]),
     "mtm_em_fit": (_i, [_vp, _i, _d, _i, _vp, _vp, ctypes.POINTER(FitInfo), ctypes.POINTER(_i64), _i]),
+    "mtm_sweep_fit": (_i, [_vp, _i, _i, _d, _i, _vp, _vp, ctypes.POINTER(FitInfo), ctypes.POINTER(_d),
+                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_i64), _i]),
     "mtm_comm_unique_id": (_i, [_vp]),
     "mtm_comm_init": (_i, [_vp, _vp, _i, _i]),
     "mtm_comm_destroy": (_i, [_vp]),

@@ -66,8 +66,9 @@ struct mtm_handle {
     int sm_count = 148;
     mtm_data data{};
     bool has_data = false;
-    Ctrl *d_ctrl = nullptr;
-    Ctrl *h_ctrl = nullptr;  // pinned
+    Ctrl *d_ctrl = nullptr;  // [ctrl_cap]: one control block per concurrently running fit
+    Ctrl *h_ctrl = nullptr;  // pinned mirror
+    int ctrl_cap = 0;
     double *d_partials = nullptr;
     size_t partials_cap = 0;
     double *d_statsbuf = nullptr;
@@ -140,13 +141,27 @@ int check_dims(mtm_handle *h, const mtm_data *dt, int n_c) {
     return 0;
 }
 
+int ensure_ctrl(mtm_handle *h, int R) {
+    if (R <= h->ctrl_cap) return 0;
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->d_ctrl) MTM_CUDA(h, cudaFree(h->d_ctrl));
+    if (h->h_ctrl) MTM_CUDA(h, cudaFreeHost(h->h_ctrl));
+    h->d_ctrl = nullptr;
+    h->h_ctrl = nullptr;
+    h->ctrl_cap = 0;
+    MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->d_ctrl), sizeof(Ctrl) * R));
+    MTM_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_ctrl), sizeof(Ctrl) * R));
+    h->ctrl_cap = R;
+    return 0;
+}
+
 bool can_fuse(const mtm_data *dt, int n_c) {
     return dt->z_dev != nullptr && estep_smem(n_c, dt->T, dt->d, dt->l, true) <= 72 * 1024;
 }
 
 int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n_c, int T0, int32_t *assign,
                   int count_switches, double *ll, double *probs, double *prenorm, unsigned long long *counts,
-                  double *score_partials, int check_done, int *grid_out, bool fused = false) {
+                  double *score_partials, int check_done, int *grid_out, bool fused = false, int R = 1) {
     EStepArgs a{};
     a.z = dt->z_dev;
     a.x = dt->x_dev;
@@ -166,11 +181,12 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
     a.counts = counts;
     a.score_partials = score_partials;
     a.check_done = check_done;
+    a.R = R;
     const int grid = estep_grid(dt->n, h->sm_count, fused);
     if (grid_out) *grid_out = grid;
     if (fused) {
         const size_t n_vals = (size_t)n_c * stats_stride(dt->d, dt->l);
-        if (int rc = ensure(h, h->d_partials, h->partials_cap, 2 * n_vals * ((size_t)grid + kReduceSlices))) return rc;
+        if (int rc = ensure(h, h->d_partials, h->partials_cap, 2 * n_vals * ((size_t)grid + kReduceSlices) * R)) return rc;
         a.stats_partials = h->d_partials;
     }
     const size_t smem = estep_smem(n_c, a.T0, a.d, a.l, fused);
@@ -189,19 +205,19 @@ int allreduce_stats(mtm_handle *h, double *buf, size_t count) {
 
 // block partials in h->d_partials (from `grid` blocks) -> h->d_statsbuf [n_c*sstride | n_switches | n_local],
 // all-reduced over the communicator
-int enqueue_stats_reduce(mtm_handle *h, int n_c, int grid, int check_done, int with_switches) {
+int enqueue_stats_reduce(mtm_handle *h, int n_c, int grid, int check_done, int with_switches, int R = 1) {
     const mtm_data &dt = h->data;
     const int n_vals = n_c * stats_stride(dt.d, dt.l);
-    if (int rc = ensure(h, h->d_statsbuf, h->statsbuf_cap, (size_t)n_vals + 2)) return rc;
+    if (int rc = ensure(h, h->d_statsbuf, h->statsbuf_cap, ((size_t)n_vals + 2) * R)) return rc;
     MTM_CUDA(h, launch_stats_reduce(h->d_partials, grid, n_vals, h->d_statsbuf,
-                                    h->d_partials + 2 * (size_t)grid * n_vals, h->d_ctrl, check_done,
-                                    with_switches ? &h->d_ctrl->n_switches : nullptr, (double)dt.n, h->stream));
+                                    h->d_partials + 2 * (size_t)R * grid * n_vals, h->d_ctrl, check_done,
+                                    with_switches, (double)dt.n, R, h->stream));
     h->launches += 2;
-    return allreduce_stats(h, h->d_statsbuf, (size_t)n_vals + 2);
+    return allreduce_stats(h, h->d_statsbuf, ((size_t)n_vals + 2) * R);
 }
 
 // statistics of the resident set under `assign` (stand-alone kernel) + reduce + all-reduce
-int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done, int with_switches) {
+int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done, int with_switches, int R = 1) {
     const mtm_data &dt = h->data;
     const size_t n_vals = (size_t)n_c * stats_stride(dt.d, dt.l);
     const int grid = stats_grid(dt.n, h->sm_count);
@@ -209,7 +225,7 @@ int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done,
     if (smem > 220 * 1024)
         return fail(h, -1, "statistics kernel needs %zu B of shared memory (n_c=%d, d=%d, l=%d): too large", smem, n_c,
                     dt.d, dt.l);
-    if (int rc = ensure(h, h->d_partials, h->partials_cap, 2 * n_vals * ((size_t)grid + kReduceSlices))) return rc;
+    if (int rc = ensure(h, h->d_partials, h->partials_cap, 2 * n_vals * ((size_t)grid + kReduceSlices) * R)) return rc;
     StatsArgs s{};
     s.z = dt.z_dev;
     s.x = dt.x_dev;
@@ -222,28 +238,29 @@ int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done,
     s.partials = h->d_partials;
     s.ctrl = h->d_ctrl;
     s.check_done = check_done;
+    s.R = R;
     MTM_CUDA(h, launch_stats(s, grid, h->stream));
     h->launches += 1;
-    return enqueue_stats_reduce(h, n_c, grid, check_done, with_switches);
+    return enqueue_stats_reduce(h, n_c, grid, check_done, with_switches, R);
 }
 
 // one EM iteration's kernels: E-step (+ fused statistics when possible) -> reduce -> all-reduce
-int enqueue_e_and_stats(mtm_handle *h, int n_c, const double *params, int32_t *assign, int check_done) {
+int enqueue_e_and_stats(mtm_handle *h, int n_c, const double *params, int32_t *assign, int check_done, int R = 1) {
     const mtm_data &dt = h->data;
     if (can_fuse(&dt, n_c)) {
         int grid = 0;
         if (int rc = enqueue_estep(h, &dt, params, n_c, dt.T, assign, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                   check_done, &grid, true))
+                                   check_done, &grid, true, R))
             return rc;
-        return enqueue_stats_reduce(h, n_c, grid, check_done, 1);
+        return enqueue_stats_reduce(h, n_c, grid, check_done, 1, R);
     }
     if (int rc = enqueue_estep(h, &dt, params, n_c, dt.T, assign, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
-                               check_done, nullptr, false))
+                               check_done, nullptr, false, R))
         return rc;
-    return enqueue_stats(h, assign, n_c, check_done, 1);
+    return enqueue_stats(h, assign, n_c, check_done, 1, R);
 }
 
-int enqueue_finalize(mtm_handle *h, int n_c, double alpha, double *params, int mode, int n_steps) {
+int enqueue_finalize(mtm_handle *h, int n_c, double alpha, double *params, int mode, int n_steps, int R = 1) {
     const mtm_data &dt = h->data;
     FinalizeArgs f{};
     f.stats = h->d_statsbuf;
@@ -257,13 +274,14 @@ int enqueue_finalize(mtm_handle *h, int n_c, double alpha, double *params, int m
     f.mode = mode;
     f.n_steps = n_steps;
     f.switch_hist = h->d_hist;
+    f.R = R;
     MTM_CUDA(h, launch_finalize(f, h->d_statsbuf + (size_t)n_c * stats_stride(dt.d, dt.l), h->stream));
     h->launches += 1;
     return 0;
 }
 
-int read_ctrl(mtm_handle *h) {
-    MTM_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+int read_ctrl(mtm_handle *h, int R = 1) {
+    MTM_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl) * R, cudaMemcpyDeviceToHost, h->stream));
     MTM_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -306,6 +324,7 @@ int mtm_create(int device, void *stream, mtm_handle **out) {
                     prop.major, prop.minor);
     }
     h->sm_count = prop.multiProcessorCount;
+    h->ctrl_cap = 1;
     bool ok = cudaMalloc(reinterpret_cast<void **>(&h->d_ctrl), sizeof(Ctrl)) == cudaSuccess &&
               cudaMallocHost(reinterpret_cast<void **>(&h->h_ctrl), sizeof(Ctrl)) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void **>(&h->d_counts), sizeof(unsigned long long) * MTM_MAX_CLUSTERS) ==
@@ -397,7 +416,7 @@ int mtm_score(mtm_handle *h, const mtm_data *data, const double *params_dev, int
     if (int rc = enqueue_estep(h, dt, params_dev, n_c, dt->T, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
                                h->d_score + 2, 0, nullptr))
         return rc;
-    MTM_CUDA(h, launch_score_reduce(h->d_score + 2, grid, h->d_score, h->stream));
+    MTM_CUDA(h, launch_score_reduce(h->d_score + 2, grid, h->d_score, 1, h->stream));
     h->launches += 1;
     if (int rc = allreduce_stats(h, h->d_score, 2)) return rc;
     MTM_CUDA(h, cudaMemcpyAsync(h->h_pin, h->d_score, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -539,6 +558,84 @@ int mtm_em_fit(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assig
         static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
         MTM_CUDA(h, cudaMemcpyAsync(switches_host, h->d_hist, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, h->stream));
         MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int mtm_sweep_fit(mtm_handle *h, int n_c, int n_restarts, double alpha, int n_steps, int32_t *assign_dev,
+                  double *params_dev, mtm_fit_info *info_host, double *scores_host, int32_t *score_status_host,
+                  int64_t *switches_host, int switches_cap) {
+    if (!h) return -1;
+    if (!h->has_data) return fail(h, -1, "no resident data set (mtm_set_data)");
+    if (int rc = check_dims(h, &h->data, n_c)) return rc;
+    if (!assign_dev || !params_dev || !info_host) return fail(h, -1, "NULL argument");
+    if (n_restarts < 1 || n_restarts > 65535) return fail(h, -1, "n_restarts=%d outside [1, 65535]", n_restarts);
+    if (n_steps < 0) return fail(h, -1, "n_steps < 0");
+    DeviceGuard g(h->device);
+    const mtm_data &dt = h->data;
+    const int R = n_restarts;
+    if (int rc = ensure_ctrl(h, R)) return rc;
+    const size_t hist_need = (size_t)R * (n_steps > 0 ? n_steps : 1);
+    if (hist_need > (size_t)h->hist_cap) {
+        if (h->d_hist) MTM_CUDA(h, cudaFree(h->d_hist));
+        h->d_hist = nullptr;
+        h->hist_cap = 0;
+        MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->d_hist), sizeof(long long) * hist_need));
+        h->hist_cap = (int)hist_need;
+    }
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl) * R, h->stream));
+    if (int rc = enqueue_stats(h, assign_dev, n_c, 0, 0, R)) return rc;
+    if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 1, n_steps, R)) return rc;
+    const int batch = ((double)dt.n * n_c * R < 2e6) ? 16 : ((double)dt.n * n_c * R < 5e7 ? 4 : 1);
+    int issued = 0;
+    auto all_done = [&]() {
+        for (int r = 0; r < R; ++r)
+            if (!h->h_ctrl[r].done) return false;
+        return true;
+    };
+    if (int rc = read_ctrl(h, R)) return rc;
+    while (!all_done() && issued < n_steps) {
+        const int nb = (n_steps - issued < batch) ? (n_steps - issued) : batch;
+        for (int b = 0; b < nb; ++b) {
+            if (int rc = enqueue_e_and_stats(h, n_c, params_dev, assign_dev, 1, R)) return rc;
+            if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 1, n_steps, R)) return rc;
+        }
+        issued += nb;
+        if (int rc = read_ctrl(h, R)) return rc;
+    }
+    for (int r = 0; r < R; ++r) {
+        const Ctrl &c = h->h_ctrl[r];
+        info_host[r].exit_code = c.exit_code;
+        info_host[r].n_e_steps = c.n_e_steps;
+        info_host[r].status = c.status;
+        info_host[r].n_m_steps = c.n_m_steps;
+        info_host[r].last_switches = c.last_switches;
+        info_host[r].min_count = c.min_count;
+    }
+    if (switches_host && switches_cap > 0 && n_steps > 0) {
+        for (int r = 0; r < R; ++r) {
+            const int m = info_host[r].n_e_steps < switches_cap ? info_host[r].n_e_steps : switches_cap;
+            if (m > 0)
+                MTM_CUDA(h, cudaMemcpyAsync(switches_host + (size_t)r * switches_cap, h->d_hist + (size_t)r * n_steps,
+                                            sizeof(int64_t) * m, cudaMemcpyDeviceToHost, h->stream));
+        }
+        MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    if (scores_host) {
+        // Q and LL of every final model in one launch (e_complete_data_log_lik per restart, MMM:1458-1461)
+        const int grid = estep_grid(dt.n, h->sm_count, false);
+        if (int rc = ensure(h, h->d_score, h->score_cap, (size_t)2 * R + 2 * (size_t)grid * R)) return rc;
+        MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl) * R, h->stream));
+        if (int rc = enqueue_estep(h, &dt, params_dev, n_c, dt.T, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                                   h->d_score + 2 * R, 0, nullptr, false, R))
+            return rc;
+        MTM_CUDA(h, launch_score_reduce(h->d_score + 2 * R, grid, h->d_score, R, h->stream));
+        h->launches += 1;
+        if (int rc = allreduce_stats(h, h->d_score, (size_t)2 * R)) return rc;
+        MTM_CUDA(h, cudaMemcpyAsync(scores_host, h->d_score, sizeof(double) * 2 * R, cudaMemcpyDeviceToHost, h->stream));
+        if (int rc = read_ctrl(h, R)) return rc;
+        if (score_status_host)
+            for (int r = 0; r < R; ++r) score_status_host[r] = h->h_ctrl[r].status;
     }
     return 0;
 }

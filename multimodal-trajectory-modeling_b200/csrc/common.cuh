@@ -38,6 +38,9 @@ struct EStepArgs {
     unsigned long long *counts;    // (n_c) cluster sizes after the E-step, nullable
     double *score_partials;        // nullable: (grid, 2) block sums of Q and LL terms
     int check_done;                // honour ctrl->done (EM loop) or not (stand-alone calls)
+    int R;                         // batched restarts: gridDim.y independent fits (0/1 = single fit); arrays
+                                   // params (R, n_c, stride), assign (R, n), ctrl [R], counts (R, MAX_CLUSTERS),
+                                   // score_partials (R, grid, 2), stats_partials (R, grid, n_c, sstride, 2)
     double *stats_partials;        // nullable: fused mode — the M-step statistics of the NEW labels are
                                    // accumulated in the same pass: (grid, n_c, sstride, 2) block sums
 };
@@ -48,9 +51,10 @@ struct StatsArgs {
     int T, d, l;
     const int32_t *assign;
     int n_c;
-    double *partials;  // (grid, n_c, sstride, 2): block sums as (hi, lo) double-double pairs
-    const Ctrl *ctrl;
+    double *partials;  // (R, grid, n_c, sstride, 2): block sums as (hi, lo) double-double pairs
+    const Ctrl *ctrl;  // [R]
     int check_done;
+    int R;             // batched restarts (gridDim.y); assign is (R, n)
 };
 
 struct FinalizeArgs {
@@ -62,7 +66,8 @@ struct FinalizeArgs {
     Ctrl *ctrl;
     int mode;  // 0: plain M-step (always write); 1: EM-loop step (decide converged / guard / continue)
     int n_steps;
-    long long *switch_hist;  // nullable
+    long long *switch_hist;  // nullable; (R, n_steps)
+    int R;                   // batched restarts: one block per restart; stats (R, n_vals + 2), params (R, n_c, pstride)
 };
 
 // launchers (one translation unit per kernel family so that nvcc can build them in parallel)
@@ -77,12 +82,12 @@ size_t stats_smem(int n_c, int d, int l);
 // `scratch` holds kReduceSlices * n_vals * 2 doubles (two-stage fixed-order reduction).
 constexpr int kReduceSlices = 16;
 cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
-                                const Ctrl *ctrl, int check_done, const unsigned long long *n_switches_src,
-                                double n_local, cudaStream_t s);
+                                const Ctrl *ctrl, int check_done, int with_switches, double n_local, int R,
+                                cudaStream_t s);
 // tail (nullable) = the two trailing slots of the all-reduced statistics buffer
 cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStream_t s);
 cudaError_t launch_counts(const int32_t *assign, int64_t n, int n_c, unsigned long long *counts, cudaStream_t s);
-cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, cudaStream_t s);
+cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, int R, cudaStream_t s);
 cudaError_t run_fp64_peak(int reps, int sm_count, cudaStream_t s, double *tflops);
 
 __host__ __device__ inline int param_stride(int d, int l) { return 1 + d + 3 * d * d + d * l + l * l; }

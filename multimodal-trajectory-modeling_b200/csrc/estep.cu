@@ -36,12 +36,12 @@ struct PSel;
 template <>
 struct PSel<true> {
     using type = ConstSrc;
-    static __device__ __forceinline__ ConstSrc get(const double *, int c, int stride) { return ConstSrc{c * stride}; }
+    static __device__ __forceinline__ ConstSrc get(const double *, int cg, int, int stride) { return ConstSrc{cg * stride}; }
 };
 template <>
 struct PSel<false> {
     using type = SmemSrc;
-    static __device__ __forceinline__ SmemSrc get(const double *s_par, int c, int stride) {
+    static __device__ __forceinline__ SmemSrc get(const double *s_par, int, int c, int stride) {
         return SmemSrc{s_par + c * stride};
     }
 };
@@ -54,7 +54,15 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     using DM = Dims<D_, L_>;
     using PS = PSel<CONSTP>;
     const DM dm{a.d, a.l};
-    if (a.check_done && a.ctrl->done) return;
+    // restart dimension (batched restarts, K4): blockIdx.y selects one independent fit — its own
+    // parameters, labels, control block and partial sums; gridDim.y = 1 everywhere else
+    const int r = blockIdx.y;
+    Ctrl *const ctrl = a.ctrl + r;
+    if (a.check_done && ctrl->done) return;
+    const double *const params = a.params + (size_t)r * a.n_c * dm.stride();
+    int32_t *const assign = a.assign ? a.assign + (size_t)r * a.n : nullptr;
+    unsigned long long *const counts = a.counts ? a.counts + (size_t)r * MTM_MAX_CLUSTERS : nullptr;
+    double *const score_partials = a.score_partials ? a.score_partials + 2 * (size_t)r * gridDim.x : nullptr;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int stride = dm.stride();
@@ -73,14 +81,14 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
 
     const int tid = threadIdx.x;
     if (!CONSTP)
-        for (int k = tid; k < a.n_c * stride; k += kEThreads) s_par[k] = a.params[k];
+        for (int k = tid; k < a.n_c * stride; k += kEThreads) s_par[k] = params[k];
     for (int k = tid; k < a.n_c; k += kEThreads) s_cnt[k] = 0;
     if (FUSE)
         for (int k = tid; k < 2 * a.n_c * stats_stride(dm.d(), dm.l()); k += kEThreads) ssm.acc[k] = 0.0;
     if (tid == 0) s_sw = 0;
     __syncthreads();
     for (int c = tid; c < a.n_c; c += kEThreads) {
-        const auto src = PS::get(s_par, c, stride);
+        const auto src = PS::get(s_par, r * a.n_c + c, c, stride);
         s_pi[c] = src[0];
         s_logpi[c] = log(src[0]);
         mean_finite_masks(dm, src, a.T0, s_fin + c * a.T0);
@@ -104,7 +112,7 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
         double best = 0.0, best_ll = 0.0, sum_l = 0.0;
         int arg = 0;
         for (int c = 0; c < a.n_c; ++c) {
-            const double ll = filter_eval<DM, HAS_Z>(dm, z_i, zs, x_i, xs, a.T0, PS::get(s_par, c, stride),
+            const double ll = filter_eval<DM, HAS_Z>(dm, z_i, zs, x_i, xs, a.T0, PS::get(s_par, r * a.n_c + c, c, stride),
                                                      s_fin + c * a.T0, bad);
             const double lc = s_pi[c] * exp(ll);
             if (valid) {
@@ -128,14 +136,14 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
                     a.probs[o] = a.probs[o] / sum_l;
                 }
             }
-            if (a.assign) {
-                if (a.count_switches) sw_acc += (a.assign[i] != arg) ? 1u : 0u;
-                a.assign[i] = arg;
+            if (assign) {
+                if (a.count_switches) sw_acc += (assign[i] != arg) ? 1u : 0u;
+                assign[i] = arg;
             }
             q_acc += s_logpi[arg] + best_ll;
             l_acc += log(sum_l);
         }
-        if (a.counts) {
+        if (counts) {
             for (int c = 0; c < a.n_c; ++c) {
                 const unsigned int m = __ballot_sync(0xffffffffu, valid && arg == c);
                 if ((tid & 31) == 0 && m) atomicAdd(&s_cnt[c], (unsigned int)__popc(m));
@@ -145,13 +153,13 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     }
 
     // block epilogue: integer counters by atomics (exact, order-free), fp64 sums in a fixed order
-    if (bad) atomicOr(&a.ctrl->status, bad);
+    if (bad) atomicOr(&ctrl->status, bad);
     if (a.count_switches) {
         MTM_UNROLL
         for (int o = 16; o > 0; o >>= 1) sw_acc += __shfl_xor_sync(0xffffffffu, sw_acc, o);
         if ((tid & 31) == 0 && sw_acc) atomicAdd(&s_sw, sw_acc);
     }
-    if (a.score_partials) {
+    if (score_partials) {
         MTM_UNROLL
         for (int o = 16; o > 0; o >>= 1) {
             q_acc += __shfl_xor_sync(0xffffffffu, q_acc, o);
@@ -164,29 +172,31 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     }
     __syncthreads();
     if (tid == 0) {
-        if (a.count_switches && s_sw) atomicAdd(&a.ctrl->n_switches, (unsigned long long)s_sw);
-        if (a.score_partials) {
+        if (a.count_switches && s_sw) atomicAdd(&ctrl->n_switches, (unsigned long long)s_sw);
+        if (score_partials) {
             double q = 0.0, l = 0.0;
             for (int w = 0; w < kEThreads / 32; ++w) {
                 q += s_red[0][w];
                 l += s_red[1][w];
             }
-            a.score_partials[2 * blockIdx.x] = q;
-            a.score_partials[2 * blockIdx.x + 1] = l;
+            score_partials[2 * blockIdx.x] = q;
+            score_partials[2 * blockIdx.x + 1] = l;
         }
     }
-    if (a.counts)
+    if (counts)
         for (int c = tid; c < a.n_c; c += kEThreads)
-            if (s_cnt[c]) atomicAdd(&a.counts[c], (unsigned long long)s_cnt[c]);
+            if (s_cnt[c]) atomicAdd(&counts[c], (unsigned long long)s_cnt[c]);
     if (FUSE) {
         const int nv = 2 * a.n_c * stats_stride(dm.d(), dm.l());
-        double *out = a.stats_partials + (size_t)blockIdx.x * nv;
+        double *out = a.stats_partials + ((size_t)r * gridDim.x + blockIdx.x) * nv;
         for (int k = tid; k < nv; k += kEThreads) out[k] = ssm.acc[k];
     }
 }
 
 // fixed-order sum of the per-block (Q, LL) partials
-__global__ void score_reduce_kernel(const double *__restrict__ partials, int grid, double *out2) {
+__global__ void score_reduce_kernel(const double *__restrict__ partials_all, int grid, double *out_all) {
+    const double *partials = partials_all + 2 * (size_t)blockIdx.x * grid;  // one block per restart
+    double *out2 = out_all + 2 * blockIdx.x;
     __shared__ double s[2][256];
     double q = 0.0, l = 0.0;
     for (int b = threadIdx.x; b < grid; b += 256) {
@@ -231,13 +241,13 @@ static cudaError_t launch_one(const EStepArgs &a, int grid, size_t smem, cudaStr
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k<<<grid, kEThreads, smem, s>>>(a);
+    k<<<dim3(grid, a.R > 1 ? a.R : 1), kEThreads, smem, s>>>(a);
     return cudaGetLastError();
 }
 
 template <int D_, int L_>
 static cudaError_t launch_dl(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
-    const size_t n_par = (size_t)a.n_c * param_stride(a.d, a.l);
+    const size_t n_par = (size_t)(a.R > 1 ? a.R : 1) * a.n_c * param_stride(a.d, a.l);
     if (D_ > 0 && n_par <= MTM_CONST_DOUBLES) {
         // stage the parameter rows in the constant bank (device -> device, stream ordered)
         cudaError_t e = cudaMemcpyToSymbolAsync(c_par, a.params, n_par * sizeof(double), 0,
@@ -270,8 +280,8 @@ cudaError_t launch_estep(const EStepArgs &a, int grid, size_t smem, cudaStream_t
 #endif
 }
 
-cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, cudaStream_t s) {
-    score_reduce_kernel<<<1, 256, 0, s>>>(partials, grid, out2);
+cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, int R, cudaStream_t s) {
+    score_reduce_kernel<<<R > 1 ? R : 1, 256, 0, s>>>(partials, grid, out2);
     return cudaGetLastError();
 }
 

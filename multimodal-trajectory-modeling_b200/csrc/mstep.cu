@@ -26,7 +26,9 @@ template <int D_, int L_>
 __global__ void __launch_bounds__(kSThreads) stats_kernel(const StatsArgs a) {
     using DM = Dims<D_, L_>;
     const DM dm{a.d, a.l};
-    if (a.check_done && a.ctrl->done) return;
+    const int r = blockIdx.y;  // batched restarts
+    if (a.check_done && a.ctrl[r].done) return;
+    const int32_t *const assign = a.assign + (size_t)r * a.n;
     const int n_c = a.n_c;
     const int sstride = stats_stride(dm.d(), dm.l());
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -41,10 +43,10 @@ __global__ void __launch_bounds__(kSThreads) stats_kernel(const StatsArgs a) {
         const int64_t i_raw = tile * kSThreads + tid;
         const bool valid = i_raw < n;
         const int64_t i = valid ? i_raw : n - 1;
-        stats_tile(dm, a.z, a.x, n, a.T, i, valid ? a.assign[i] : -1, n_c, sm);
+        stats_tile(dm, a.z, a.x, n, a.T, i, valid ? assign[i] : -1, n_c, sm);
     }
     __syncthreads();
-    double *out = a.partials + 2 * (size_t)blockIdx.x * n_c * sstride;
+    double *out = a.partials + 2 * ((size_t)r * gridDim.x + blockIdx.x) * n_c * sstride;
     for (int k = tid; k < 2 * n_c * sstride; k += kSThreads) out[k] = sm.acc[k];
 }
 
@@ -53,9 +55,12 @@ __global__ void __launch_bounds__(kSThreads) stats_kernel(const StatsArgs a) {
 //  stage 2: thread v adds the S slices in order                                  -> out[v]
 // tail slots: out[n_vals] = n_switches of the preceding E-step (exact integer as double),
 //             out[n_vals+1] = local n
-__global__ void stats_reduce1_kernel(const double *__restrict__ partials, int grid, int n_vals, double *scratch,
-                                     const Ctrl *ctrl, int check_done) {
-    if (check_done && ctrl->done) return;
+__global__ void stats_reduce1_kernel(const double *__restrict__ partials_all, int grid, int n_vals,
+                                     double *scratch_all, const Ctrl *ctrl, int check_done) {
+    const int r = blockIdx.z;  // batched restarts
+    if (check_done && ctrl[r].done) return;
+    const double *partials = partials_all + 2 * (size_t)r * grid * n_vals;
+    double *scratch = scratch_all + 2 * (size_t)r * gridDim.y * n_vals;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y, S = gridDim.y;
     if (v >= n_vals) return;
@@ -68,10 +73,13 @@ __global__ void stats_reduce1_kernel(const double *__restrict__ partials, int gr
     *reinterpret_cast<double2 *>(scratch + 2 * ((size_t)s * n_vals + v)) = make_double2(hi, lo);
 }
 
-__global__ void stats_reduce2_kernel(const double *__restrict__ scratch, int S, int n_vals, double *out,
-                                     const Ctrl *ctrl, int check_done, const unsigned long long *n_switches_src,
-                                     double n_local) {
-    if (check_done && ctrl->done) return;
+__global__ void stats_reduce2_kernel(const double *__restrict__ scratch_all, int S, int n_vals, double *out_all,
+                                     const Ctrl *ctrl, int check_done, int with_switches, double n_local) {
+    const int r = blockIdx.y;
+    if (check_done && ctrl[r].done) return;
+    const double *scratch = scratch_all + 2 * (size_t)r * S * n_vals;
+    double *out = out_all + (size_t)r * (n_vals + 2);
+    const unsigned long long *n_switches_src = with_switches ? &ctrl[r].n_switches : nullptr;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v < n_vals) {
         double hi = 0.0, lo = 0.0;
@@ -191,12 +199,18 @@ __device__ int regress_from_moments(const double *blk, int p, int q, double alph
     return status;
 }
 
-__global__ void finalize_kernel(const FinalizeArgs a, const double *tail) {
-    Ctrl *ctrl = a.ctrl;
+__global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
+    const int r = blockIdx.x;  // batched restarts: one block per fit
+    FinalizeArgs a = a0;
+    Ctrl *ctrl = a0.ctrl + r;
     if (a.mode == 1 && ctrl->done) return;
     const int d = a.d, l = a.l, n_c = a.n_c;
     const int F1 = 1 + d + d * (d + 1) / 2, F2 = 1 + 2 * d + d * (2 * d + 1);
     const int sstride = stats_stride(d, l), pstride = param_stride(d, l);
+    a.stats = a0.stats + (size_t)r * ((size_t)n_c * sstride + (tail0 ? 2 : 0));
+    a.params = a0.params + (size_t)r * n_c * pstride;
+    a.switch_hist = a0.switch_hist ? a0.switch_hist + (size_t)r * a.n_steps : nullptr;
+    const double *tail = tail0 ? a.stats + (size_t)n_c * sstride : nullptr;
     __shared__ int s_go;
     __shared__ int s_status;
     if (threadIdx.x == 0) {
@@ -318,7 +332,7 @@ static cudaError_t launch_stats_dl(const StatsArgs &a, int grid, cudaStream_t s)
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k<<<grid, kSThreads, smem, s>>>(a);
+    k<<<dim3(grid, a.R > 1 ? a.R : 1), kSThreads, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -337,18 +351,20 @@ cudaError_t launch_stats(const StatsArgs &a, int grid, cudaStream_t s) {
 }
 
 cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
-                                const Ctrl *ctrl, int check_done, const unsigned long long *n_switches_src,
-                                double n_local, cudaStream_t s) {
+                                const Ctrl *ctrl, int check_done, int with_switches, double n_local, int R,
+                                cudaStream_t s) {
     const int threads = 128;
     const int S = grid >= 4 * kReduceSlices ? kReduceSlices : 1;
-    const dim3 g1((n_vals + threads - 1) / threads, S);
+    const int RR = R > 1 ? R : 1;
+    const dim3 g1((n_vals + threads - 1) / threads, S, RR);
     stats_reduce1_kernel<<<g1, threads, 0, s>>>(partials, grid, n_vals, scratch, ctrl, check_done);
-    stats_reduce2_kernel<<<g1.x, threads, 0, s>>>(scratch, S, n_vals, out, ctrl, check_done, n_switches_src, n_local);
+    stats_reduce2_kernel<<<dim3(g1.x, RR), threads, 0, s>>>(scratch, S, n_vals, out, ctrl, check_done, with_switches,
+                                                             n_local);
     return cudaGetLastError();
 }
 
 cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStream_t s) {
-    finalize_kernel<<<1, 64, 0, s>>>(a, tail);
+    finalize_kernel<<<a.R > 1 ? a.R : 1, 64, 0, s>>>(a, tail);
     return cudaGetLastError();
 }
 

@@ -170,6 +170,32 @@ class Engine:
                             last_switches=int(info.last_switches), min_count=int(info.min_count),
                             switches=[int(hist[k]) for k in range(min(cap, int(info.n_e_steps)))])
 
+    def sweep_fit(self, data: DeviceData, assign, n_c, alpha, n_steps, want_scores=True):
+        """Batched restarts (mtm_sweep_fit): assign is an (R, n) int32 device tensor, updated in place.
+        Returns (params (R, n_c, stride), infos [R dicts], scores (R, 2) ndarray or None, score_status)."""
+        self._sync_stream()
+        self.bind(data)
+        R = int(assign.shape[0])
+        params = torch.full((R, n_c, self.param_stride(data.d, data.l)), float("nan"), dtype=torch.float64,
+                            device=self.device)
+        infos = (C.FitInfo * R)()
+        scores = (ctypes.c_double * (2 * R))() if want_scores else None
+        sstat = (ctypes.c_int32 * R)() if want_scores else None
+        cap = max(1, int(n_steps))
+        hist = (ctypes.c_int64 * (cap * R))()
+        self._chk(self.lib.mtm_sweep_fit(self.h, n_c, R, float(alpha), int(n_steps), ctypes.c_void_p(assign.data_ptr()),
+                                         ctypes.c_void_p(params.data_ptr()), infos, scores, sstat, hist, cap))
+        out = []
+        for r in range(R):
+            i = infos[r]
+            out.append(dict(exit_code=int(i.exit_code), exit=C.EXIT_NAMES.get(int(i.exit_code), "?"),
+                            n_e_steps=int(i.n_e_steps), n_m_steps=int(i.n_m_steps), status=int(i.status),
+                            last_switches=int(i.last_switches), min_count=int(i.min_count),
+                            switches=[int(hist[r * cap + k]) for k in range(min(cap, int(i.n_e_steps)))]))
+        sc = np.array(scores[:], dtype=np.float64).reshape(R, 2) if want_scores else None
+        ss = np.array(sstat[:], dtype=np.int32) if want_scores else None
+        return params, out, sc, ss
+
     def fp64_peak(self, reps=10):
         self._sync_stream()
         out = ctypes.c_double(0.0)

@@ -463,16 +463,18 @@ class MMLinGaussSS_marginalizable:
             pass
         if return_objectives:
             objective_list = [best_mdl.e_complete_data_log_lik()]
+        # The n_starts random restarts are independent given the data: they run as ONE batched fit
+        # (mtm_sweep_fit: every kernel of an EM iteration serves all still-running restarts), then the
+        # reference's sequential selection is replayed on the results.
+        restarts = self._batched_random_restarts(shared, n_starts, n_steps) if n_starts > 0 else []
         for i in range(n_starts):
             try:
-                mix_mdl = MMLinGaussSS_marginalizable(n_clusters=self.n_clusters, states=self.states,
-                                                      observations=self.observations, random_seed=100 + i,
-                                                      alpha=self.alpha, device=self._device,
-                                                      _shared_data=shared).train(verbose=verbose, n_steps=n_steps)
+                status, q_i, make = restarts[i]
+                _raise_for_status(status, self.alpha)  # a failed start raises inside train() in the reference
                 if return_objectives:
-                    objective_list.append(mix_mdl.e_complete_data_log_lik())
-                if mix_mdl.e_complete_data_log_lik() > best_mdl.e_complete_data_log_lik():
-                    best_mdl = mix_mdl
+                    objective_list.append(q_i)
+                if q_i > best_mdl.e_complete_data_log_lik():
+                    best_mdl = make()
             except Exception:  # noqa: BLE001,S110
                 pass
         if not np.isfinite(best_mdl.e_complete_data_log_lik()):
@@ -482,6 +484,38 @@ class MMLinGaussSS_marginalizable:
         if return_objectives:
             return best_mdl, np.array(objective_list)
         return best_mdl
+
+    def _batched_random_restarts(self, shared, n_starts, n_steps):
+        """[(status, Q, factory)] for seeds 100 .. 100+n_starts-1 (MMM:1449-1455), fitted together."""
+        eng = self.engine
+        n, k = self.n_data, self.n_clusters
+        a0 = np.stack([np.random.default_rng(seed=100 + i).integers(low=0, high=k, size=n)
+                       for i in range(n_starts)]).astype(np.int32)
+        assign = torch.from_numpy(a0).to(eng.device)
+        params, infos, scores, sstat = eng.sweep_fit(shared, assign, k, self.alpha, n_steps)
+        params_h, assign_h = params.cpu().numpy(), assign.cpu().numpy()
+        out = []
+        for i in range(n_starts):
+            info = infos[i]
+
+            def make(i=i, info=info):
+                mdl = MMLinGaussSS_marginalizable(n_clusters=k, states=self.states, observations=self.observations,
+                                                  random_seed=100 + i, alpha=self.alpha, device=self._device,
+                                                  _shared_data=shared)
+                mdl.cluster_assignment = assign_h[i].astype(np.int64)
+                mdl.fit_info = info
+                if info["exit"] != "guard0":
+                    mdl._unpack_params(params_h[i])
+                    mdl.last_trained = (datetime.datetime.now(datetime.timezone.utc).replace(microsecond=0)
+                                        .astimezone().isoformat())
+                return mdl
+
+            status = info["status"] | int(sstat[i])
+            # a start that never trained (near-empty cluster at once) keeps the constructor's unseeded random
+            # parameters in the reference; its Q is irreproducible noise there and NaN (never selected) here
+            q_i = float(scores[i, 0]) if info["exit"] != "guard0" else float("nan")
+            out.append((status, q_i, make))
+        return out
 
     # ------------------------------------------------------------------ persistence (MMM:227-319)
     def to_pickle(self, save_location=None, there_can_only_be_one: bool = True, include_training_data: bool = False):
