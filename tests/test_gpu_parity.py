@@ -386,3 +386,50 @@ def test_pickle_roundtrip(mix, tmp_path):
     assert back.hex_hash == mdl.hex_hash
     assert np.array_equal(back._packed_params(), mdl._packed_params())
     assert np.array_equal(back.mle_cluster_assignment(), mdl.mle_cluster_assignment())
+
+
+def test_batched_restarts_equal_sequential(mix, eng):
+    """mtm_sweep_fit (kernel 4): R restarts fitted in lock-step give, restart by restart, exactly what R
+    separate mtm_em_fit calls give (same kernels, one grid row per restart), including restarts that
+    stop early while others keep iterating, and the per-restart Q / LL."""
+    import mtm_b200
+
+    z, x = _synthetic(3000, 6, 3, 3, 3, seed=21)
+    n_c, R, n_steps = 3, 12, 40
+    data = mtm_b200.DeviceData(z, x, eng.device)
+    a0 = np.stack([np.random.default_rng(100 + r).integers(0, n_c, z.shape[1]) for r in range(R)]).astype(np.int32)
+    a0[5, :] = 0
+    a0[5, :3] = [1, 2, 2]  # restart 5: near-empty clusters from the start -> guard0, nothing runs
+    batch = torch.from_numpy(a0).to(eng.device)
+    P, infos, scores, sstat = eng.sweep_fit(data, batch, n_c, 0.0, n_steps)
+    exits = set()
+    for r in range(R):
+        single = torch.from_numpy(a0[r].copy()).to(eng.device)
+        p1, i1 = eng.em_fit(data, single, n_c, 0.0, n_steps)
+        assert i1["exit"] == infos[r]["exit"] and i1["switches"] == infos[r]["switches"], (r, i1, infos[r])
+        assert torch.equal(single, batch[r])
+        exits.add(i1["exit"])
+        if i1["exit"] == "guard0":
+            assert bool(torch.isnan(P[r]).all())
+            continue
+        assert torch.equal(p1, P[r])
+        q, ll, st = eng.score(data, p1, n_c)
+        assert (q, ll) == (scores[r, 0], scores[r, 1]) and st == int(sstat[r])
+    assert "guard0" in exits and "converged" in exits
+    assert len({i["n_e_steps"] for i in infos}) > 2  # restarts really stopped at different iterations
+
+
+def test_model_selection_sweep(mix):
+    """model-selection.py:45-72 on the batched path: AIC/BIC/Q per n_c are those of the selected models."""
+    from mtm_b200 import sweep
+
+    z, x = _synthetic(1500, 5, 2, 3, 3, seed=33, sep=0.8)
+    table, models = sweep.select_n_clusters(z, x, range(1, 5), n_starts=4, n_steps=30)
+    assert list(table["n_clusters"]) == [1, 2, 3, 4]
+    for k, n_c in enumerate(range(1, 5)):
+        m = models[n_c]
+        assert table["n_free_params"][k] == m.n_free_params
+        assert abs(table["aic"][k] - (-2 * m.model_log_likelihood() + 2 * m.n_free_params)) < 1e-6
+        assert np.isfinite(table["bic"][k]) and np.isfinite(table["Q"][k])
+    # more clusters never lower the selected Q on this well-separated 3-cluster data up to the truth
+    assert table["Q"][2] > table["Q"][0]
