@@ -49,7 +49,11 @@ struct PSel<false> {
 // FUSE: the sufficient statistics of the M-step (stats_tile.cuh) are accumulated for the labels
 // this very pass assigns, while the tile's trajectories are still hot in L1/L2 and the FP64 work of
 // the other resident blocks hides the latency: one HBM pass per EM iteration instead of two.
-template <int D_, int L_, bool HAS_Z, bool CONSTP, bool FUSE>
+//
+// Fusion is a RUN-TIME switch (a.stats_partials != nullptr) on purpose: with it as a template flag the
+// non-fused instantiation happened to fall back to vector-register parameter loads (ptxas 12.9
+// heuristics, see the note at MTM_E_BOUNDS); one code shape for both keeps the uniform-datapath form.
+template <int D_, int L_, bool HAS_Z, bool CONSTP>
 __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     using DM = Dims<D_, L_>;
     using PS = PSel<CONSTP>;
@@ -71,7 +75,9 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     double *s_pi = s_logpi + a.n_c;                                       // n_c
     uint32_t *s_fin = reinterpret_cast<uint32_t *>(s_pi + a.n_c);         // n_c * T0
     unsigned int *s_cnt = s_fin + a.n_c * a.T0;                           // n_c
+    const bool FUSE = a.stats_partials != nullptr;  // block-uniform
     StatsSmem ssm;
+    ssm.acc = nullptr;
     if (FUSE) {
         const size_t eb = ((reinterpret_cast<unsigned char *>(s_cnt + a.n_c) - smem_raw) + 15) & ~size_t(15);
         ssm.carve(smem_raw + eb, a.n_c, dm.d(), dm.l());
@@ -234,9 +240,9 @@ int estep_grid(int64_t n, int sm_count, bool fused) {
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
-template <int D_, int L_, bool HAS_Z, bool CONSTP, bool FUSE = false>
+template <int D_, int L_, bool HAS_Z, bool CONSTP>
 static cudaError_t launch_one(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
-    auto k = estep_kernel<D_, L_, HAS_Z, CONSTP, FUSE>;
+    auto k = estep_kernel<D_, L_, HAS_Z, CONSTP>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -253,10 +259,8 @@ static cudaError_t launch_dl(const EStepArgs &a, int grid, size_t smem, cudaStre
         cudaError_t e = cudaMemcpyToSymbolAsync(c_par, a.params, n_par * sizeof(double), 0,
                                                 cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
-        if (a.stats_partials) return launch_one<D_, L_, true, true, true>(a, grid, smem, s);
         return a.z ? launch_one<D_, L_, true, true>(a, grid, smem, s) : launch_one<D_, L_, false, true>(a, grid, smem, s);
     }
-    if (a.stats_partials) return launch_one<D_, L_, true, false, true>(a, grid, smem, s);
     return a.z ? launch_one<D_, L_, true, false>(a, grid, smem, s) : launch_one<D_, L_, false, false>(a, grid, smem, s);
 }
 

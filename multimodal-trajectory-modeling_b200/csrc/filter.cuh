@@ -220,14 +220,16 @@ __device__ __forceinline__ void filter_condition_z(const DM &dm, FilterState<DM>
             MTM_UNROLL
             for (int i = 0; i < DM::DM; ++i)
                 if (i < d) col[i] = symget(f.P, i, j);
+            // Row / column j of P and mu[j] are not updated here: when the coordinate is present they are
+            // replaced below by exact values (0 and y), when it is missing the gain is 0 anyway.
             MTM_UNROLL
             for (int i = 0; i < DM::DM; ++i) {
-                if (i < d) {
+                if (i < d && i != j) {
                     const double g = col[i] * r;
                     f.mu[i] = fma(g, v, f.mu[i]);
                     MTM_UNROLL
                     for (int b = i; b < DM::DM; ++b)
-                        if (b < d) f.P[i][b] = fma(-g, col[b], f.P[i][b]);
+                        if (b < d && b != j) f.P[i][b] = fma(-g, col[b], f.P[i][b]);
                 }
             }
             // the conditioned coordinate is now known exactly
