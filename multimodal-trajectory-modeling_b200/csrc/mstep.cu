@@ -103,43 +103,85 @@ constexpr int MX = MTM_MAX_DIM;
 
 __device__ inline double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
+// Compile-time (P_, Q_ > 0: everything unrolled, matrices in registers) or run-time sizes.
+template <int P_, int Q_>
+struct RegDims {
+    static constexpr bool kStatic = (P_ > 0);
+    static constexpr int PM = kStatic ? P_ : MX;
+    static constexpr int QM = kStatic ? Q_ : MX;
+    int p_rt, q_rt;
+    __device__ __forceinline__ int p() const { return kStatic ? P_ : p_rt; }
+    __device__ __forceinline__ int q() const { return kStatic ? Q_ : q_rt; }
+};
+
 // Cholesky solve of (M + alpha I) B = R for SPD M (p x p), R (p x q); M is overwritten by the factor.
 // returns false if a pivot is not positive.
-__device__ bool chol_solve(double (*M)[MX], double (*R)[MX], int p, int q, double alpha) {
-    for (int i = 0; i < p; ++i) M[i][i] += alpha;
-    for (int j = 0; j < p; ++j) {
-        double s = M[j][j];
-        for (int k = 0; k < j; ++k) s -= M[j][k] * M[j][k];
-        if (!(s > 0.0)) return false;
-        const double dj = sqrt(s);
-        M[j][j] = dj;
-        for (int i = j + 1; i < p; ++i) {
-            double t = M[i][j];
-            for (int k = 0; k < j; ++k) t -= M[i][k] * M[j][k];
-            M[i][j] = t / dj;
+template <class RD>
+__device__ __forceinline__ bool chol_solve(const RD &rd, double (&M)[RD::PM][RD::PM], double (&R)[RD::PM][RD::QM],
+                                           double alpha) {
+    const int p = rd.p(), q = rd.q();
+    bool ok = true;
+    MTM_UNROLL
+    for (int j = 0; j < RD::PM; ++j) {
+        if (j < p) {
+            double s = M[j][j] + alpha;
+            MTM_UNROLL
+            for (int k = 0; k < RD::PM; ++k)
+                if (k < j) s -= M[j][k] * M[j][k];
+            ok = ok && (s > 0.0);
+            const double dj = sqrt(s);
+            M[j][j] = dj;
+            const double inv = 1.0 / dj;
+            MTM_UNROLL
+            for (int i = 0; i < RD::PM; ++i) {
+                if (i > j && i < p) {
+                    double t = M[i][j];
+                    MTM_UNROLL
+                    for (int k = 0; k < RD::PM; ++k)
+                        if (k < j) t -= M[i][k] * M[j][k];
+                    M[i][j] = t * inv;
+                }
+            }
         }
     }
-    for (int c = 0; c < q; ++c) {
-        for (int i = 0; i < p; ++i) {
-            double t = R[i][c];
-            for (int k = 0; k < i; ++k) t -= M[i][k] * R[k][c];
-            R[i][c] = t / M[i][i];
-        }
-        for (int i = p - 1; i >= 0; --i) {
-            double t = R[i][c];
-            for (int k = i + 1; k < p; ++k) t -= M[k][i] * R[k][c];
-            R[i][c] = t / M[i][i];
+    MTM_UNROLL
+    for (int c = 0; c < RD::QM; ++c) {
+        if (c < q) {
+            MTM_UNROLL
+            for (int i = 0; i < RD::PM; ++i) {
+                if (i < p) {
+                    double t = R[i][c];
+                    MTM_UNROLL
+                    for (int k = 0; k < RD::PM; ++k)
+                        if (k < i) t -= M[i][k] * R[k][c];
+                    R[i][c] = t / M[i][i];
+                }
+            }
+            MTM_UNROLL
+            for (int ii = 0; ii < RD::PM; ++ii) {
+                const int i = RD::PM - 1 - ii;
+                if (i < p) {
+                    double t = R[i][c];
+                    MTM_UNROLL
+                    for (int k = 0; k < RD::PM; ++k)
+                        if (k > i && k < p) t -= M[k][i] * R[k][c];
+                    R[i][c] = t / M[i][i];
+                }
+            }
         }
     }
-    return true;
+    return ok;
 }
 
 // moments block [cnt | sum v (K) | upper(sum vv')] of v = [a (p) | b (q)] ->
 //   B = argmin |b - a B|^2 + alpha |B|^2 (p x q), Cov = cov(b - a B) with mean removed and N-1
 // (regress / regress_alpha, MMM:1167-1233)
-__device__ int regress_from_moments(const double *blk, int p, int q, double alpha, double *B_out /*p*q*/,
-                                    double *C_out /*q*q*/) {
+template <class RD>
+__device__ __forceinline__ int regress_from_moments(const RD &rd, const double *blk, double alpha, double *B_out,
+                                                    double *C_out) {
+    const int p = rd.p(), q = rd.q();
     const int K = p + q;
+    constexpr int KM = RD::PM + RD::QM;
     const double cnt = blk[0];
     const double *sv = blk + 1;
     const double *up = blk + 1 + K;
@@ -149,62 +191,109 @@ __device__ int regress_from_moments(const double *blk, int p, int q, double alph
         for (int k = 0; k < q * q; ++k) C_out[k] = qnan();
         return MTM_STATUS_EMPTY_FIT;
     }
-    double full[2 * MX][2 * MX];
+    double full[KM][KM];
     {
         int o = 0;
-        for (int a = 0; a < K; ++a)
-            for (int b = a; b < K; ++b) {
-                full[a][b] = up[o];
-                full[b][a] = up[o];
-                ++o;
+        MTM_UNROLL
+        for (int a = 0; a < KM; ++a) {
+            if (a < K) {
+                MTM_UNROLL
+                for (int b = a; b < KM; ++b)
+                    if (b < K) {
+                        full[a][b] = up[o + (b - a)];
+                        full[b][a] = up[o + (b - a)];
+                    }
+                o += K - a;
             }
+        }
     }
-    double M[MX][MX], B[MX][MX];
-    for (int i = 0; i < p; ++i) {
-        for (int j = 0; j < p; ++j) M[i][j] = full[i][j];
-        for (int c = 0; c < q; ++c) B[i][c] = full[i][p + c];
+    double M[RD::PM][RD::PM], B[RD::PM][RD::QM];
+    MTM_UNROLL
+    for (int i = 0; i < RD::PM; ++i) {
+        if (i < p) {
+            MTM_UNROLL
+            for (int j = 0; j < RD::PM; ++j)
+                if (j < p) M[i][j] = full[i][j];
+            MTM_UNROLL
+            for (int c = 0; c < RD::QM; ++c)
+                if (c < q) B[i][c] = full[i][p + c];
+        }
     }
-    if (!chol_solve(M, B, p, q, alpha)) {
+    if (!chol_solve(rd, M, B, alpha)) {
         status |= MTM_STATUS_CHOL_FAIL;
-        for (int i = 0; i < p; ++i)
-            for (int c = 0; c < q; ++c) B[i][c] = qnan();
+        MTM_UNROLL
+        for (int i = 0; i < RD::PM; ++i)
+            MTM_UNROLL
+            for (int c = 0; c < RD::QM; ++c) B[i][c] = qnan();
     }
-    // mean residual and residual second moment
-    double rbar[MX];
-    for (int c = 0; c < q; ++c) {
-        double s = sv[p + c];
-        for (int i = 0; i < p; ++i) s -= sv[i] * B[i][c];
-        rbar[c] = s / cnt;
+    // mean residual
+    double rbar[RD::QM];
+    MTM_UNROLL
+    for (int c = 0; c < RD::QM; ++c) {
+        if (c < q) {
+            double s = sv[p + c];
+            MTM_UNROLL
+            for (int i = 0; i < RD::PM; ++i)
+                if (i < p) s -= sv[i] * B[i][c];
+            rbar[c] = s / cnt;
+        }
     }
     // E = Sxy - Sxx B (zero for least squares up to rounding, alpha B for ridge)
-    double E[MX][MX];
-    for (int i = 0; i < p; ++i)
-        for (int c = 0; c < q; ++c) {
-            double s = full[i][p + c];
-            for (int k = 0; k < p; ++k) s -= full[i][k] * B[k][c];
-            E[i][c] = s;
+    double E[RD::PM][RD::QM];
+    MTM_UNROLL
+    for (int i = 0; i < RD::PM; ++i) {
+        if (i < p) {
+            MTM_UNROLL
+            for (int c = 0; c < RD::QM; ++c) {
+                if (c < q) {
+                    double s = full[i][p + c];
+                    MTM_UNROLL
+                    for (int k = 0; k < RD::PM; ++k)
+                        if (k < p) s -= full[i][k] * B[k][c];
+                    E[i][c] = s;
+                }
+            }
         }
-    for (int a = 0; a < q; ++a)
-        for (int b = a; b < q; ++b) {
-            // SSR = Syy - B'Sxy - E'B
-            double s = full[p + a][p + b];
-            for (int i = 0; i < p; ++i) s -= B[i][a] * full[i][p + b];
-            for (int i = 0; i < p; ++i) s -= E[i][a] * B[i][b];
-            double v = (cnt > 1.0) ? (s - cnt * rbar[a] * rbar[b]) / (cnt - 1.0) : qnan();
-            C_out[a * q + b] = v;
-            C_out[b * q + a] = v;
+    }
+    MTM_UNROLL
+    for (int a = 0; a < RD::QM; ++a) {
+        if (a < q) {
+            MTM_UNROLL
+            for (int b = a; b < RD::QM; ++b) {
+                if (b < q) {
+                    // SSR = Syy - B'Sxy - E'B
+                    double s = full[p + a][p + b];
+                    MTM_UNROLL
+                    for (int i = 0; i < RD::PM; ++i)
+                        if (i < p) s -= B[i][a] * full[i][p + b];
+                    MTM_UNROLL
+                    for (int i = 0; i < RD::PM; ++i)
+                        if (i < p) s -= E[i][a] * B[i][b];
+                    const double v = (cnt > 1.0) ? (s - cnt * rbar[a] * rbar[b]) / (cnt - 1.0) : qnan();
+                    C_out[a * q + b] = v;
+                    C_out[b * q + a] = v;
+                }
+            }
         }
-    for (int i = 0; i < p; ++i)
-        for (int c = 0; c < q; ++c) B_out[i * q + c] = B[i][c];
+    }
+    MTM_UNROLL
+    for (int i = 0; i < RD::PM; ++i) {
+        if (i < p) {
+            MTM_UNROLL
+            for (int c = 0; c < RD::QM; ++c)
+                if (c < q) B_out[i * q + c] = B[i][c];
+        }
+    }
     return status;
 }
 
+template <int D_, int L_>
 __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
     const int r = blockIdx.x;  // batched restarts: one block per fit
     FinalizeArgs a = a0;
     Ctrl *ctrl = a0.ctrl + r;
     if (a.mode == 1 && ctrl->done) return;
-    const int d = a.d, l = a.l, n_c = a.n_c;
+    const int d = D_ > 0 ? D_ : a.d, l = D_ > 0 ? L_ : a.l, n_c = a.n_c;
     const int F1 = 1 + d + d * (d + 1) / 2, F2 = 1 + 2 * d + d * (2 * d + 1);
     const int sstride = stats_stride(d, l), pstride = param_stride(d, l);
     a.stats = a0.stats + (size_t)r * ((size_t)n_c * sstride + (tail0 ? 2 : 0));
@@ -214,10 +303,8 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
     __shared__ int s_go;
     __shared__ int s_status;
     if (threadIdx.x == 0) {
-        const double n_total = tail ? tail[1] : (double)a.n_total;
         double mn = 1e300;
         for (int c = 0; c < n_c; ++c) mn = fmin(mn, a.stats[(size_t)c * sstride]);
-        (void)n_total;
         int go = 1;
         s_status = 0;
         if (a.mode == 1) {
@@ -259,21 +346,23 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
     __syncthreads();
     if (!s_go) return;
 
-    for (int c = threadIdx.x; c < n_c; c += blockDim.x) {
+    // one thread per (cluster, block of the parameter row): 0 = pi, m, S; 1 = A, Gamma; 2 = H, Lambda
+    for (int task = threadIdx.x; task < 3 * n_c; task += blockDim.x) {
+        const int c = task / 3, part = task - 3 * c;
         const double *st = a.stats + (size_t)c * sstride;
         double *pr = a.params + (size_t)c * pstride;
         const double n_total = tail ? tail[1] : (double)a.n_total;
         int status = 0;
-        pr[0] = st[0] / n_total;  // pi_c = mean(assign == c)
-        // initial state: mean and np.cov(ddof=1) of the finite z_1 rows
-        const double *b1 = st + 1;
-        const double n0 = b1[0];
-        double m[MX];
-        for (int i = 0; i < d; ++i) {
-            m[i] = b1[1 + i] / n0;  // 0/0 = NaN for an empty sample, like np.mean
-            pr[1 + i] = m[i];
-        }
-        {
+        if (part == 0) {
+            pr[0] = st[0] / n_total;  // pi_c = mean(assign == c)
+            // initial state: mean and np.cov(ddof=1) of the finite z_1 rows
+            const double *b1 = st + 1;
+            const double n0 = b1[0];
+            double m[MX];
+            for (int i = 0; i < d; ++i) {
+                m[i] = b1[1 + i] / n0;  // 0/0 = NaN for an empty sample, like np.mean
+                pr[1 + i] = m[i];
+            }
             int o = 1 + d;
             double *S = pr + 1 + d;
             for (int i = 0; i < d; ++i)
@@ -283,10 +372,15 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
                     S[j * d + i] = v;
                     ++o;
                 }
+        } else if (part == 1) {
+            double *A = pr + 1 + d + d * d, *G = A + d * d;
+            const RegDims<D_, D_> rd{d, d};
+            status |= regress_from_moments(rd, st + 1 + F1, a.alpha, A, G);
+        } else {
+            double *H = pr + 1 + d + 3 * d * d, *Lam = H + d * l;
+            const RegDims<D_, L_> rd{d, l};
+            status |= regress_from_moments(rd, st + 1 + F1 + F2, a.alpha, H, Lam);
         }
-        double *A = pr + 1 + d + d * d, *G = A + d * d, *H = G + d * d, *Lam = H + d * l;
-        status |= regress_from_moments(st + 1 + F1, d, d, a.alpha, A, G);
-        status |= regress_from_moments(st + 1 + F1 + F2, d, l, a.alpha, H, Lam);
         if (status) atomicOr(&s_status, status);
     }
     __syncthreads();
@@ -364,7 +458,23 @@ cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, do
 }
 
 cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStream_t s) {
-    finalize_kernel<<<a.R > 1 ? a.R : 1, 64, 0, s>>>(a, tail);
+    const int blocks = a.R > 1 ? a.R : 1;
+    int threads = 32;
+    while (threads < 3 * a.n_c && threads < 256) threads *= 2;
+#define MTM_CASE(DD, LL)                                             \
+    if (a.d == DD && a.l == LL) {                                    \
+        finalize_kernel<DD, LL><<<blocks, threads, 0, s>>>(a, tail); \
+        return cudaGetLastError();                                   \
+    }
+    MTM_CASE(4, 4)
+    MTM_CASE(2, 4)
+    MTM_CASE(2, 3)
+    MTM_CASE(1, 1)
+    MTM_CASE(3, 3)
+    MTM_CASE(2, 2)
+    MTM_CASE(5, 3)
+#undef MTM_CASE
+    finalize_kernel<0, 0><<<blocks, threads, 0, s>>>(a, tail);
     return cudaGetLastError();
 }
 
