@@ -9,6 +9,10 @@
 
 #include "common.cuh"
 
+#ifndef MTM_CONST_DOUBLES
+#define MTM_CONST_DOUBLES 7680  // capacity of the constant-bank parameter store (filter.cuh)
+#endif
+
 using namespace mtm;
 
 // ---- minimal NCCL surface, resolved at run time from the libnccl.so.2 already in the process ----
@@ -191,8 +195,26 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
     }
     const size_t smem = estep_smem(n_c, a.T0, a.d, a.l, fused);
     if (smem > 200 * 1024) return fail(h, -1, "E-step shared memory %zu B too large (n_c * T0 too big)", smem);
-    MTM_CUDA(h, launch_estep(a, grid, smem, h->stream));
-    h->launches += 1;
+    // Batched restarts on a large data set: launch in chunks of restarts whose parameter rows fit the
+    // constant bank together, so that every chunk runs the fast uniform-operand kernel; for small data
+    // sets (launch-latency bound) one launch serves all restarts from shared-memory parameter copies.
+    const size_t row = (size_t)n_c * param_stride(a.d, a.l);
+    int chunk = R;
+    if (R > 1 && row * R > MTM_CONST_DOUBLES && row <= MTM_CONST_DOUBLES && (double)dt->n * n_c >= 2e6)
+        chunk = (int)(MTM_CONST_DOUBLES / row);
+    const size_t nv2 = fused ? 2 * (size_t)n_c * stats_stride(dt->d, dt->l) : 0;
+    for (int r0 = 0; r0 < R; r0 += chunk) {
+        EStepArgs b = a;
+        b.R = (R - r0 < chunk) ? (R - r0) : chunk;
+        b.params = a.params + (size_t)r0 * row;
+        b.ctrl = a.ctrl + r0;
+        if (a.assign) b.assign = a.assign + (size_t)r0 * dt->n;
+        if (a.counts) b.counts = a.counts + (size_t)r0 * MTM_MAX_CLUSTERS;
+        if (a.score_partials) b.score_partials = a.score_partials + 2 * (size_t)r0 * grid;
+        if (a.stats_partials) b.stats_partials = a.stats_partials + (size_t)r0 * grid * nv2;
+        MTM_CUDA(h, launch_estep(b, grid, smem, h->stream));
+        h->launches += 1;
+    }
     return 0;
 }
 
