@@ -369,7 +369,11 @@ def main():
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     bpt = bytes_per_traj(args.T, args.d, args.l)
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp64_peak, "traffic": None,
+                "frac": achieved_tf / fp64_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+                # (profiles/r1d_fused_ncu_summary.md: 1.0373 GB + 23.5 MB for 2 M trajectories = 530.4 B per
+                # trajectory), scaled to this launch's trajectory count
+                "traffic": 530.4 * n_loc, "traffic_unit": "bytes per launch (ncu-measured 530.4 B/trajectory x n)",
                 "kernel": "estep_kernel<4,4,HAS_Z,CONSTP,FUSE> (E-step + fused M-step statistics; the timed span also "
                           "holds the two ~10 us reduction kernels and, for N > 1, the all-reduce)",
                 "kernel_ms": ms_e,
