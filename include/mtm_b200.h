@@ -71,6 +71,9 @@ typedef struct {
     int32_t d;
     int32_t l;
     int32_t reserved;
+    int64_t ld; /* trajectories per time step in memory: element (t, i, j) of z sits at z_dev[(t*ld + i)*d + j].
+                   0 means ld = n (contiguous).  ld > n addresses a slab of trajectories inside a larger
+                   (T, ld, d) buffer without repacking. */
 } mtm_data;
 
 typedef struct {
@@ -154,6 +157,21 @@ int mtm_mstep(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, d
  * only exists so that a benchmark can time the dominant kernel on its own).  Synchronises if info != NULL. */
 int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, double *params_dev, int phases,
                 mtm_estep_info *info);
+
+/* ---- one EM iteration, end to end from HOST buffers -----------------------------------------------
+ * Same result as mtm_em_step(phases = 3) on data that lives in host memory (pinned for full PCIe rate):
+ * the trajectory axis is cut into n_slabs slabs; slab k+1 is uploaded on a private copy stream
+ * (2-D copies straight into its place in the (T, n, d|l) device buffers, no repacking) while slab k runs
+ * the fused E-step + statistics kernel, and slab k's new labels are downloaded while slab k+1 computes.
+ *   z_host, x_host      (T, n, d|l) float64 host arrays;  z_dev, x_dev: device buffers of the same shape
+ *   assign_host         (n) int32 in/out (old labels in, new labels out);  assign_dev: (n) int32 device scratch
+ *   params_dev          (n_c, param_stride) in/out: parameters of the previous iteration in, new ones out
+ *   params_host         (n_c, param_stride) out
+ *   info                nullable: n_switches, min_count, status.   Synchronises. */
+int mtm_em_step_host(mtm_handle *h, const double *z_host, const double *x_host, int T, int64_t n, int d, int l,
+                     double *z_dev, double *x_dev, int n_c, double alpha, int32_t *assign_host,
+                     int32_t *assign_dev, double *params_dev, double *params_host, int n_slabs,
+                     mtm_estep_info *info);
 
 /* ---- EM fit --------------------------------------------------------------------------------------
  * train (MMM:1310-1366) on the resident set, loop resident on the device:

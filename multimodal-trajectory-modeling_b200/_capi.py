@@ -32,7 +32,8 @@ class MtmError(RuntimeError):
 
 class MtmData(ctypes.Structure):
     _fields_ = [("z_dev", ctypes.c_void_p), ("x_dev", ctypes.c_void_p), ("n", ctypes.c_int64),
-                ("T", ctypes.c_int32), ("d", ctypes.c_int32), ("l", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("T", ctypes.c_int32), ("d", ctypes.c_int32), ("l", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("ld", ctypes.c_int64)]
 
 
 class EStepInfo(ctypes.Structure):
@@ -62,6 +63,8 @@ SIGNATURES = {
     "mtm_finalize": (_i, [_vp, _vp, _i, _i, _i, _i64, _d, _vp, _vp]),
     "mtm_mstep": (_i, [_vp, _vp, _i, _d, _vp, ctypes.POINTER(EStepInfo)]),
     "mtm_em_step": (_i, [_vp, _i, _d, _vp, _vp, _i, ctypes.POINTER(EStepInfo)]),
+    "mtm_em_step_host": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _i,
+                              ctypes.POINTER(EStepInfo)]),
     "mtm_em_fit": (_i, [_vp, _i, _d, _i, _vp, _vp, ctypes.POINTER(FitInfo), ctypes.POINTER(_i64), _i]),
     "mtm_sweep_fit": (_i, [_vp, _i, _i, _d, _i, _vp, _vp, ctypes.POINTER(FitInfo), ctypes.POINTER(_d),
                            ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_i64), _i]),

@@ -84,6 +84,12 @@ struct mtm_handle {
     long long *d_hist = nullptr;
     int hist_cap = 0;
     double *h_pin = nullptr;  // small pinned scratch (16 doubles)
+    cudaStream_t copy_stream = nullptr;  // private upload stream of the host-streaming path
+    cudaStream_t down_stream = nullptr;  // private download stream (PCIe is full duplex)
+    cudaEvent_t ev_up[64] = {};          // slab k uploaded
+    cudaEvent_t ev_done[64] = {};        // slab k computed
+    cudaEvent_t ev_free = nullptr;       // staging buffers free again (previous step finished)
+    bool stream_ready = false;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
     std::string err;
@@ -138,6 +144,7 @@ int check_dims(mtm_handle *h, const mtm_data *dt, int n_c) {
     if (dt->d < 1 || dt->d > MTM_MAX_DIM || dt->l < 1 || dt->l > MTM_MAX_DIM)
         return fail(h, -1, "dimensions d=%d l=%d outside [1, %d]", dt->d, dt->l, MTM_MAX_DIM);
     if (dt->T < 1 || dt->n < 1) return fail(h, -1, "empty data set (T=%d, n=%lld)", dt->T, (long long)dt->n);
+    if (dt->ld != 0 && dt->ld < dt->n) return fail(h, -1, "ld=%lld smaller than n=%lld", (long long)dt->ld, (long long)dt->n);
     if (n_c < 1 || n_c > MTM_MAX_CLUSTERS) return fail(h, -1, "n_c=%d outside [1, %d]", n_c, MTM_MAX_CLUSTERS);
     if ((dt->d % 2 == 0 && dt->z_dev && (reinterpret_cast<uintptr_t>(dt->z_dev) & 15)) ||
         (dt->l % 2 == 0 && (reinterpret_cast<uintptr_t>(dt->x_dev) & 15)))
@@ -170,6 +177,7 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
     a.z = dt->z_dev;
     a.x = dt->x_dev;
     a.n = dt->n;
+    a.ld = dt->ld > 0 ? dt->ld : dt->n;
     a.T = dt->T;
     a.T0 = T0 < 1 ? 1 : (T0 > dt->T ? dt->T : T0);
     a.d = dt->d;
@@ -252,6 +260,7 @@ int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done,
     s.z = dt.z_dev;
     s.x = dt.x_dev;
     s.n = dt.n;
+    s.ld = dt.ld > 0 ? dt.ld : dt.n;
     s.T = dt.T;
     s.d = dt.d;
     s.l = dt.l;
@@ -368,6 +377,15 @@ int mtm_destroy(mtm_handle *h) {
     if (!h) return 0;
     DeviceGuard g(h->device);
     if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+    if (h->stream_ready) {
+        for (int k = 0; k < 64; ++k) {
+            cudaEventDestroy(h->ev_up[k]);
+            cudaEventDestroy(h->ev_done[k]);
+        }
+        cudaEventDestroy(h->ev_free);
+        cudaStreamDestroy(h->copy_stream);
+        cudaStreamDestroy(h->down_stream);
+    }
     cudaFree(h->d_ctrl);
     cudaFreeHost(h->h_ctrl);
     cudaFree(h->d_partials);
@@ -526,6 +544,111 @@ int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, doubl
     }
     if (info) {
         if (int rc = read_ctrl(h)) return rc;
+        info->n_switches = (int64_t)h->h_ctrl->n_switches;
+        info->min_count = h->h_ctrl->min_count;
+        info->status = h->h_ctrl->status;
+        info->reserved = 0;
+    }
+    return 0;
+}
+
+int mtm_em_step_host(mtm_handle *h, const double *z_host, const double *x_host, int T, int64_t n, int d, int l,
+                     double *z_dev, double *x_dev, int n_c, double alpha, int32_t *assign_host,
+                     int32_t *assign_dev, double *params_dev, double *params_host, int n_slabs,
+                     mtm_estep_info *info) {
+    if (!h) return -1;
+    if (!z_host || !x_host || !z_dev || !x_dev || !assign_host || !assign_dev || !params_dev || !params_host)
+        return fail(h, -1, "NULL argument");
+    mtm_data full{};
+    full.z_dev = z_dev;
+    full.x_dev = x_dev;
+    full.n = n;
+    full.T = T;
+    full.d = d;
+    full.l = l;
+    if (int rc = check_dims(h, &full, n_c)) return rc;
+    if (!can_fuse(&full, n_c)) return fail(h, -1, "configuration too large for the fused kernel (n_c=%d)", n_c);
+    if (n_slabs < 1) n_slabs = 1;
+    if (n_slabs > 64) n_slabs = 64;
+    if ((int64_t)n_slabs * 128 > n) n_slabs = (int)((n + 127) / 128);
+    DeviceGuard g(h->device);
+    if (!h->stream_ready) {
+        MTM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        MTM_CUDA(h, cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 64; ++k) {
+            MTM_CUDA(h, cudaEventCreateWithFlags(&h->ev_up[k], cudaEventDisableTiming));
+            MTM_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
+        }
+        MTM_CUDA(h, cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
+        h->stream_ready = true;
+    }
+    h->data = full;  // reductions and finalise read the dimensions of the resident set
+    h->has_data = true;
+    const int sstride = stats_stride(d, l);
+    const size_t n_vals = (size_t)n_c * sstride;
+    // slab boundaries on 128-trajectory tiles (16-byte alignment of every slab start follows)
+    const int64_t tiles = (n + 127) / 128;
+    int grids[64];
+    int64_t start[65];
+    int grid_total = 0;
+    for (int k = 0; k <= n_slabs; ++k) {
+        const int64_t t0 = tiles * k / n_slabs;
+        start[k] = t0 * 128 < n ? t0 * 128 : n;
+    }
+    start[n_slabs] = n;
+    for (int k = 0; k < n_slabs; ++k) {
+        grids[k] = estep_grid(start[k + 1] - start[k], h->sm_count, true);
+        grid_total += grids[k];
+    }
+    if (int rc = ensure(h, h->d_partials, h->partials_cap, 2 * n_vals * ((size_t)grid_total + kReduceSlices))) return rc;
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    // the staging buffers may still be read by work enqueued before this call
+    MTM_CUDA(h, cudaEventRecord(h->ev_free, h->stream));
+    MTM_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free, 0));
+    int goff = 0;
+    for (int k = 0; k < n_slabs; ++k) {
+        const int64_t s0 = start[k], ns = start[k + 1] - start[k];
+        // upload slab k: T rows of ns*d (ns*l) doubles, pitch n*d (n*l) doubles on both sides
+        MTM_CUDA(h, cudaMemcpy2DAsync(z_dev + s0 * d, (size_t)n * d * 8, z_host + s0 * d, (size_t)n * d * 8,
+                                      (size_t)ns * d * 8, T, cudaMemcpyHostToDevice, h->copy_stream));
+        MTM_CUDA(h, cudaMemcpy2DAsync(x_dev + s0 * l, (size_t)n * l * 8, x_host + s0 * l, (size_t)n * l * 8,
+                                      (size_t)ns * l * 8, T, cudaMemcpyHostToDevice, h->copy_stream));
+        MTM_CUDA(h, cudaMemcpyAsync(assign_dev + s0, assign_host + s0, (size_t)ns * 4, cudaMemcpyHostToDevice,
+                                    h->copy_stream));
+        MTM_CUDA(h, cudaEventRecord(h->ev_up[k], h->copy_stream));
+        MTM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_up[k], 0));
+        EStepArgs a{};
+        a.z = z_dev + s0 * d;
+        a.x = x_dev + s0 * l;
+        a.n = ns;
+        a.ld = n;
+        a.T = T;
+        a.T0 = T;
+        a.d = d;
+        a.l = l;
+        a.params = params_dev;
+        a.n_c = n_c;
+        a.assign = assign_dev + s0;
+        a.count_switches = 1;
+        a.ctrl = h->d_ctrl;
+        a.R = 1;
+        a.stats_partials = h->d_partials + 2 * n_vals * (size_t)goff;
+        MTM_CUDA(h, launch_estep(a, grids[k], estep_smem(n_c, T, d, l, true), h->stream));
+        h->launches += 1;
+        goff += grids[k];
+        // download slab k's labels while the next slab computes
+        MTM_CUDA(h, cudaEventRecord(h->ev_done[k], h->stream));
+        MTM_CUDA(h, cudaStreamWaitEvent(h->down_stream, h->ev_done[k], 0));
+        MTM_CUDA(h, cudaMemcpyAsync(assign_host + s0, assign_dev + s0, (size_t)ns * 4, cudaMemcpyDeviceToHost,
+                                    h->down_stream));
+    }
+    if (int rc = enqueue_stats_reduce(h, n_c, grid_total, 0, 1, 1)) return rc;
+    if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 0, 0, 1)) return rc;
+    MTM_CUDA(h, cudaMemcpyAsync(params_host, params_dev, (size_t)n_c * param_stride(d, l) * 8, cudaMemcpyDeviceToHost,
+                                h->stream));
+    if (int rc = read_ctrl(h)) return rc;
+    MTM_CUDA(h, cudaStreamSynchronize(h->down_stream));
+    if (info) {
         info->n_switches = (int64_t)h->h_ctrl->n_switches;
         info->min_count = h->h_ctrl->min_count;
         info->status = h->h_ctrl->status;

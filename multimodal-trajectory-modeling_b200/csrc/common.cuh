@@ -28,6 +28,7 @@ struct EStepArgs {
     const double *z;  // (T, n, d) or nullptr
     const double *x;  // (T, n, l)
     int64_t n;
+    int64_t ld;  // trajectories per time step in memory (>= n): step stride is ld*d / ld*l doubles
     int T, T0, d, l;
     const double *params;  // (n_c, stride)
     int n_c;
@@ -48,6 +49,7 @@ struct EStepArgs {
 struct StatsArgs {
     const double *z, *x;
     int64_t n;
+    int64_t ld;  // trajectories per time step in memory (>= n)
     int T, d, l;
     const int32_t *assign;
     int n_c;

@@ -103,7 +103,7 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
 
     const int64_t n = a.n;
     const int64_t n_tiles = (n + kEThreads - 1) / kEThreads;
-    const int64_t zs = n * dm.d(), xs = n * dm.l();
+    const int64_t zs = a.ld * dm.d(), xs = a.ld * dm.l();
     double q_acc = 0.0, l_acc = 0.0;
     unsigned int sw_acc = 0;
     int bad = 0;
@@ -155,7 +155,7 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
                 if ((tid & 31) == 0 && m) atomicAdd(&s_cnt[c], (unsigned int)__popc(m));
             }
         }
-        if (FUSE) stats_tile(dm, a.z, a.x, n, a.T, i, valid ? arg : -1, a.n_c, ssm);
+        if (FUSE) stats_tile(dm, a.z, a.x, a.ld, a.T, i, valid ? arg : -1, a.n_c, ssm);
     }
 
     // block epilogue: integer counters by atomics (exact, order-free), fp64 sums in a fixed order

@@ -113,7 +113,7 @@ __host__ __device__ inline size_t stats_smem_bytes(int n_c, int d, int l) {
 // trajectory i (any value outside [0, n_c) = not counted), `i` a valid (clamped) trajectory index.
 template <class DM>
 __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restrict__ z, const double *__restrict__ x,
-                                           int64_t n, int T, int64_t i, int label, int n_c, const StatsSmem &sm) {
+                                           int64_t ld, int T, int64_t i, int label, int n_c, const StatsSmem &sm) {
     const int d = dm.d(), l = dm.l();
     constexpr int DMX = DM::DM, LMX = DM::LM;
     constexpr int K1 = DMX, K2 = 2 * DMX, K3 = DMX + LMX;
@@ -123,7 +123,7 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
     const int sstride = 1 + F1 + F2 + F3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kSThreads / 32;
-    const int64_t zs = n * d, xs = n * l;
+    const int64_t zs = ld * d, xs = ld * l;
     double *s_acc = sm.acc, *s_feat = sm.feat;
     int *s_list = sm.list, *s_start = sm.start, *s_wcnt = sm.wcnt;
     if (label < 0 || label >= n_c) label = -1;

@@ -170,6 +170,30 @@ class Engine:
                             last_switches=int(info.last_switches), min_count=int(info.min_count),
                             switches=[int(hist[k]) for k in range(min(cap, int(info.n_e_steps)))])
 
+    def em_step(self, data: DeviceData, assign, params, n_c, alpha, want_info=True):
+        """One EM iteration on resident data (the reference's E_step(); M_step() pair): assign and params
+        (device tensors) are updated in place.  Returns (n_switches, min_count, status) if want_info."""
+        self._sync_stream()
+        self.bind(data)
+        info = C.EStepInfo()
+        self._chk(self.lib.mtm_em_step(self.h, n_c, float(alpha), ctypes.c_void_p(assign.data_ptr()),
+                                       ctypes.c_void_p(params.data_ptr()), 3, ctypes.byref(info) if want_info else None))
+        return (int(info.n_switches), int(info.min_count), int(info.status)) if want_info else None
+
+    def em_step_host(self, z_host, x_host, z_dev, x_dev, assign_host, assign_dev, params_dev, params_host, n_c, alpha,
+                     n_slabs=16):
+        """One EM iteration end to end from (pinned) host tensors: slab-pipelined upload, fused E-step +
+        statistics per slab, labels streamed back, parameters solved and downloaded (mtm_em_step_host)."""
+        self._sync_stream()
+        T, n, d = (int(v) for v in z_host.shape)
+        l = int(x_host.shape[2])
+        info = C.EStepInfo()
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        self._chk(self.lib.mtm_em_step_host(self.h, p(z_host), p(x_host), T, n, d, l, p(z_dev), p(x_dev), n_c,
+                                            float(alpha), p(assign_host), p(assign_dev), p(params_dev), p(params_host),
+                                            int(n_slabs), ctypes.byref(info)))
+        return int(info.n_switches), int(info.min_count), int(info.status)
+
     def sweep_fit(self, data: DeviceData, assign, n_c, alpha, n_steps, want_scores=True):
         """Batched restarts (mtm_sweep_fit): assign is an (R, n) int32 device tensor, updated in place.
         Returns (params (R, n_c, stride), infos [R dicts], scores (R, 2) ndarray or None, score_status)."""

@@ -433,3 +433,32 @@ def test_model_selection_sweep(mix):
         assert np.isfinite(table["bic"][k]) and np.isfinite(table["Q"][k])
     # more clusters never lower the selected Q on this well-separated 3-cluster data up to the truth
     assert table["Q"][2] > table["Q"][0]
+
+
+def test_host_streamed_step_equals_resident_step(eng):
+    """mtm_em_step_host (slab-pipelined upload) == mtm_em_step on resident data: labels and switch count
+    bit-exact, parameters to rounding (the block-partial grouping differs), for ragged slab sizes."""
+    import mtm_b200
+
+    n, T, d, l, n_c = 70_003, 6, 4, 4, 5
+    z, x = _synthetic(n, T, d, l, n_c, seed=77)
+    dev = eng.device
+    data = mtm_b200.DeviceData(z, x, dev)
+    a0 = np.random.default_rng(3).integers(0, n_c, n).astype(np.int32)
+    a_res = torch.from_numpy(a0.copy()).to(dev)
+    p_res, _, _ = eng.mstep(data, a_res, n_c, 0.0)
+    p_host_dev = p_res.clone()
+    sw_res, mc_res, st_res = eng.em_step(data, a_res, p_res, n_c, 0.0)
+    zh, xh = torch.from_numpy(z).pin_memory(), torch.from_numpy(x).pin_memory()
+    ah = torch.from_numpy(a0.copy()).pin_memory()
+    ph = torch.empty(p_res.shape, dtype=torch.float64).pin_memory()
+    zd, xd = torch.full_like(data.z, float("nan")), torch.full_like(data.x, float("nan"))
+    ad = torch.empty(n, dtype=torch.int32, device=dev)
+    for n_slabs in (1, 7, 16):
+        ah.copy_(torch.from_numpy(a0))
+        pd = p_host_dev.clone()
+        sw, mc, st = eng.em_step_host(zh, xh, zd, xd, ah, ad, pd, ph, n_c, 0.0, n_slabs=n_slabs)
+        assert (sw, mc, st) == (sw_res, mc_res, st_res)
+        assert np.array_equal(ah.numpy(), a_res.cpu().numpy())
+        assert relerr(ph.numpy(), p_res.cpu().numpy()) < 1e-12
+        assert torch.equal(pd.cpu(), ph)
