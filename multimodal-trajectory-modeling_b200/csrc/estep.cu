@@ -76,12 +76,8 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     uint32_t *s_fin = reinterpret_cast<uint32_t *>(s_pi + a.n_c);         // n_c * T0
     unsigned int *s_cnt = s_fin + a.n_c * a.T0;                           // n_c
     const bool FUSE = a.stats_partials != nullptr;  // block-uniform
-    StatsSmem ssm;
-    ssm.acc = nullptr;
-    if (FUSE) {
-        const size_t eb = ((reinterpret_cast<unsigned char *>(s_cnt + a.n_c) - smem_raw) + 15) & ~size_t(15);
-        ssm.carve(smem_raw + eb, a.n_c, dm.d(), dm.l());
-    }
+    unsigned char *const stats_base =
+        smem_raw + (((reinterpret_cast<unsigned char *>(s_cnt + a.n_c) - smem_raw) + 15) & ~size_t(15));
     __shared__ double s_red[2][kEThreads / 32];
     __shared__ unsigned int s_sw;
 
@@ -90,7 +86,8 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
         for (int k = tid; k < a.n_c * stride; k += kEThreads) s_par[k] = params[k];
     for (int k = tid; k < a.n_c; k += kEThreads) s_cnt[k] = 0;
     if (FUSE)
-        for (int k = tid; k < 2 * a.n_c * stats_stride(dm.d(), dm.l()); k += kEThreads) ssm.acc[k] = 0.0;
+        for (int k = tid; k < 2 * a.n_c * stats_stride(dm.d(), dm.l()); k += kEThreads)
+            reinterpret_cast<double *>(stats_base)[k] = 0.0;
     if (tid == 0) s_sw = 0;
     __syncthreads();
     for (int c = tid; c < a.n_c; c += kEThreads) {
@@ -119,7 +116,7 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
         int arg = 0;
         for (int c = 0; c < a.n_c; ++c) {
             const double ll = filter_eval<DM, HAS_Z>(dm, z_i, zs, x_i, xs, a.T0, PS::get(s_par, r * a.n_c + c, c, stride),
-                                                     s_fin + c * a.T0, bad);
+                                                     s_fin + c * a.T0, bad, a.tshift);
             const double lc = s_pi[c] * exp(ll);
             if (valid) {
                 if (a.ll) a.ll[(int64_t)c * n + i] = ll;
@@ -155,7 +152,7 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
                 if ((tid & 31) == 0 && m) atomicAdd(&s_cnt[c], (unsigned int)__popc(m));
             }
         }
-        if (FUSE) stats_tile(dm, a.z, a.x, a.ld, a.T, i, valid ? arg : -1, a.n_c, ssm);
+        if (FUSE) stats_tile(dm, a.z, a.x, a.ld, a.T, i, valid ? arg : -1, a.n_c, stats_base);
     }
 
     // block epilogue: integer counters by atomics (exact, order-free), fp64 sums in a fixed order
@@ -195,7 +192,7 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     if (FUSE) {
         const int nv = 2 * a.n_c * stats_stride(dm.d(), dm.l());
         double *out = a.stats_partials + ((size_t)r * gridDim.x + blockIdx.x) * nv;
-        for (int k = tid; k < nv; k += kEThreads) out[k] = ssm.acc[k];
+        for (int k = tid; k < nv; k += kEThreads) out[k] = reinterpret_cast<const double *>(stats_base)[k];
     }
 }
 

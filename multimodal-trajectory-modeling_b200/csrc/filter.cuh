@@ -79,11 +79,13 @@ __constant__ double c_par[MTM_CONST_DOUBLES];
 struct ConstSrc {
     int base;
     __device__ __forceinline__ double operator[](int k) const { return c_par[base + k]; }
+    __device__ __forceinline__ ConstSrc shifted(int o) const { return ConstSrc{base + o}; }
 };
 #endif
 struct SmemSrc {
     const double *row;
     __device__ __forceinline__ double operator[](int k) const { return row[k]; }
+    __device__ __forceinline__ SmemSrc shifted(int o) const { return SmemSrc{row + o}; }
 };
 
 template <class DM, class PS>
@@ -385,16 +387,25 @@ __device__ __forceinline__ void load_row(const double *__restrict__ p, double (&
 
 // One full evaluation.  z_i / x_i point at step 0 of trajectory i; zs / xs = step strides in doubles.
 // fin[t] = bit mask of finite unconditional means at step t: bits [0, d) for z, [16, 16 + l) for x.
+// `tshift` is a kernel argument that is ZERO at run time.  The parameter offsets of step t are formed as
+// base + t * tshift: still warp-uniform (so the loads go through the uniform datapath, LDCU -> UR
+// operands), but formally dependent on t, which keeps ptxas from hoisting the loop-invariant parameter
+// loads out of the time loop into ~100 vector registers (what it does otherwise whenever it finds the
+// registers, and what costs the register-file read bandwidth the DFMA stream needs).
 template <class DM, bool HAS_Z, class PS>
 __device__ __forceinline__ double filter_eval(const DM &dm, const double *__restrict__ z_i, int64_t zs,
                                               const double *__restrict__ x_i, int64_t xs, int T0,
-                                              const PS &psrc, const uint32_t *fin, int &bad) {
-    const ParamView<DM, PS> p(dm, psrc);
+                                              const PS &psrc, const uint32_t *fin, int &bad, int tshift) {
     FilterState<DM> f;
-    filter_init(dm, f, p);
+    {
+        const ParamView<DM, PS> p0(dm, psrc);
+        filter_init(dm, f, p0);
+    }
     double zt[DM::DM], xt[DM::LM];
     if (HAS_Z) load_row<DM::DM>(z_i, zt, dm.d(), DM::kStatic);
     load_row<DM::LM>(x_i, xt, dm.l(), DM::kStatic);
+    (void)tshift;
+    const ParamView<DM, PS> p(dm, psrc);
     for (int t = 0; t < T0; ++t) {
         // software pipeline: issue the loads of step t+1 before the arithmetic of step t
         double zn[DM::DM], xn[DM::LM];

@@ -55,30 +55,39 @@ __device__ __forceinline__ bool all_finite(const double (&v)[NM], int n) {
 
 // block-level reduce-by-cluster of per-trajectory features that sit in registers
 //   feat[f] (f < F) of thread tid -> s_feat[f * ST + tid]; task (c, f) sums the members of c.
+// block-level reduce-by-cluster of per-trajectory features that sit in registers.
+//   `pos` = the thread's position in the tile's cluster-sorted order (-1: not counted).  The features
+//   are staged ALREADY SORTED (s_feat[f * ST + pos]), so the members of cluster c are the contiguous
+//   range [start[c], start[c+1]) of every feature row: task (c, f) adds them with independent,
+//   address-predictable loads (no index indirection), four interleaved chains in a fixed pattern.
 template <int FM>
-__device__ __forceinline__ void reduce_by_cluster(const double *feat, int F, double *s_feat, const int *s_list,
+__device__ __forceinline__ void reduce_by_cluster(const double *feat, int F, double *s_feat, int pos,
                                                   const int *s_start, int n_c, double *s_acc, int sstride,
                                                   int gofs) {
     constexpr int ST = kSThreads + 1;
     const int tid = threadIdx.x;
-    MTM_UNROLL
-    for (int f = 0; f < FM; ++f)
-        if (f < F) s_feat[f * ST + tid] = feat[f];
+    if (pos >= 0) {
+        MTM_UNROLL
+        for (int f = 0; f < FM; ++f)
+            if (f < F) s_feat[f * ST + pos] = feat[f];
+    }
     __syncthreads();
     for (int task = tid; task < n_c * F; task += kSThreads) {
         const int c = task / F, f = task - c * F;
         const int b = s_start[c], e = s_start[c + 1];
         if (e > b) {
             const double *row = s_feat + f * ST;
-            double s0 = 0.0, s1 = 0.0;  // two interleaved chains in a fixed pattern
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int r = b;
-            for (; r + 1 < e; r += 2) {
-                s0 += row[s_list[r]];
-                s1 += row[s_list[r + 1]];
+            for (; r + 3 < e; r += 4) {
+                s0 += row[r];
+                s1 += row[r + 1];
+                s2 += row[r + 2];
+                s3 += row[r + 3];
             }
-            if (r < e) s0 += row[s_list[r]];
+            for (; r < e; ++r) s0 += row[r];
             double *acc = s_acc + 2 * ((size_t)c * sstride + gofs + f);
-            dd_add(acc[0], acc[1], s0 + s1);
+            dd_add(acc[0], acc[1], (s0 + s1) + (s2 + s3));
         }
     }
     __syncthreads();
@@ -113,7 +122,11 @@ __host__ __device__ inline size_t stats_smem_bytes(int n_c, int d, int l) {
 // trajectory i (any value outside [0, n_c) = not counted), `i` a valid (clamped) trajectory index.
 template <class DM>
 __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restrict__ z, const double *__restrict__ x,
-                                           int64_t ld, int T, int64_t i, int label, int n_c, const StatsSmem &sm) {
+                                           int64_t ld, int T, int64_t i, int label, int n_c, unsigned char *smem_base) {
+    // carved here, per call, from ONE base pointer: keeping five derived pointers alive across the caller's
+    // E-step loop costs uniform registers that the parameter operands of that loop need
+    StatsSmem sm;
+    sm.carve(smem_base, n_c, dm.d(), dm.l());
     const int d = dm.d(), l = dm.l();
     constexpr int DMX = DM::DM, LMX = DM::LM;
     constexpr int K1 = DMX, K2 = 2 * DMX, K3 = DMX + LMX;
@@ -125,7 +138,7 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
     constexpr int NW = kSThreads / 32;
     const int64_t zs = ld * d, xs = ld * l;
     double *s_acc = sm.acc, *s_feat = sm.feat;
-    int *s_list = sm.list, *s_start = sm.start, *s_wcnt = sm.wcnt;
+    int *s_start = sm.start, *s_wcnt = sm.wcnt;
     if (label < 0 || label >= n_c) label = -1;
 
     // ---- stable counting sort of the tile's labels -> member lists ----
@@ -145,10 +158,11 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
         s_start[n_c] = run;
     }
     __syncthreads();
+    int pos = -1;  // position of this trajectory in the cluster-sorted order of the tile
     if (label >= 0) {
         int off = s_start[label];
         for (int w = 0; w < warp; ++w) off += s_wcnt[w * n_c + label];
-        s_list[off + my_rank] = tid;
+        pos = off + my_rank;
     }
     // cluster sizes: exact integers, carried as doubles (< 2^53)
     for (int c = tid; c < n_c; c += kSThreads) {
@@ -159,6 +173,9 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
     const double *z_i = z + i * d;
     const double *x_i = x + i * l;
 
+    // NOTE: the two passes deliberately load each step right before its use.  A one-step-ahead software
+    // prefetch here (tried) made ptxas 12.9 drop the uniform-datapath parameter operands of the E-step time
+    // loop this code is inlined behind (tools/sass_reuse.py: 0.89 -> 0.79), a net loss.
     // ---- pass 1: initial-state and transition moments ----
     {
         double f1[F1M], f2[F2M];
@@ -185,8 +202,8 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
             for (int k = 0; k < DMX; ++k) zc[k] = zn[k];
             okc = okn;
         }
-        reduce_by_cluster<F1M>(f1, F1, s_feat, s_list, s_start, n_c, s_acc, sstride, 1);
-        reduce_by_cluster<F2M>(f2, F2, s_feat, s_list, s_start, n_c, s_acc, sstride, 1 + F1);
+        reduce_by_cluster<F1M>(f1, F1, s_feat, pos, s_start, n_c, s_acc, sstride, 1);
+        reduce_by_cluster<F2M>(f2, F2, s_feat, pos, s_start, n_c, s_acc, sstride, 1 + F1);
     }
     // ---- pass 2: measurement moments ----
     {
@@ -207,7 +224,7 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
                 if (k < l) w[d + k] = xc[k];
             add_moments<K3>(f3, w, d + l, ok && label >= 0);
         }
-        reduce_by_cluster<F3M>(f3, F3, s_feat, s_list, s_start, n_c, s_acc, sstride, 1 + F1 + F2);
+        reduce_by_cluster<F3M>(f3, F3, s_feat, pos, s_start, n_c, s_acc, sstride, 1 + F1 + F2);
     }
 }
 

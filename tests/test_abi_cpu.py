@@ -97,3 +97,27 @@ def test_state_space_helpers(g_ssm):
         assert np.allclose(ssm.CC(T, g("S"), g("A"), g("G"), g("H"), g("L")), g("cov"), rtol=1e-12, atol=1e-12)
         assert np.allclose(ssm.mmX(T, g("m"), g("A"), g("H")), g("meanx"), rtol=1e-12, atol=1e-12)
         assert np.allclose(ssm.CXX(T, g("S"), g("A"), g("G"), g("H"), g("L")), g("covx"), rtol=1e-12, atol=1e-12)
+
+
+def test_headline_kernel_keeps_uniform_parameter_operands():
+    """Regression guard for the E-step code shape: in the (d, l) = (4, 4) kernel the
+    model parameters must reach the DFMAs as uniform-register operands.  tools/sass_reuse.py models the
+    vector-register reads per FP64 instruction of the time loop from the SASS: ~0.89 in the intended form,
+    ~0.79 when ptxas falls back to vector-register parameter loads."""
+    import shutil
+    import subprocess
+    import sys
+
+    import mtm_b200
+
+    obj = os.path.join(ROOT, "multimodal-trajectory-modeling_b200", "csrc", "_build", "estep.o")
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(obj):
+        mtm_b200.build()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_reuse.py"), obj, "ILi4ELi4ELb1ELb1E"],
+                         capture_output=True, text=True, check=True).stdout
+    eff = float(re.search(r"pipe efficiency ([0-9.]+)", out).group(1))
+    assert eff >= 0.85, out
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    assert re.search(r"DFMA R\d+, R\d+(\.reuse)?, UR\d+, R", sass), "no uniform-register DFMA operands"
