@@ -368,9 +368,33 @@ def golden_adni(ssm, mmm, uss):
     print("adni_fold0.npz written; objectives", obj)
 
 
+# ---------------------------------------------------------------------------
+# 5. framework_extended linear-Gaussian component
+# ---------------------------------------------------------------------------
+
+
+def golden_lg_component(ssm):
+    from framework_extended import state_space_model_linear_gaussian as ssm_lg
+
+    out = {}
+    rng = np.random.default_rng(2024)
+    for tag, alpha in (("a0", 0.0), ("a1", 0.5)):
+        z, x, lab, comps = sample_mixture(ssm, rng, 500, 6, 3, 4, 1, 0.15, 1.0)
+        mdl = ssm_lg.StateSpaceLinearGaussian(alpha=alpha).fit((z, x))
+        zt, xt = z[:, :200].copy(), x[:, :200].copy()
+        zt[rng.random(zt.shape) < 0.2] = np.nan
+        for k, v in dict(z=z, x=x, alpha=alpha, mean=mdl.state_init["mean"], cov=mdl.state_init["cov"],
+                         A=mdl.state_model["coeff"], G=mdl.state_model["covar"], H=mdl.measurement_model["coeff"],
+                         L=mdl.measurement_model["covar"], score=mdl.score(), zt=zt, xt=xt,
+                         score_t=mdl.score((zt, xt))).items():
+            out[f"{tag}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "lg_component.npz"), **out)
+    print("lg_component.npz written")
+
+
 if __name__ == "__main__":
     ssm, mmm, uss = import_reference()
-    which = sys.argv[1:] or ["ssm", "em", "restarts", "adni"]
+    which = sys.argv[1:] or ["ssm", "em", "restarts", "adni", "lg"]
     if "ssm" in which:
         golden_ssm(ssm)
     if "em" in which:
@@ -379,3 +403,5 @@ if __name__ == "__main__":
         golden_restarts(ssm, mmm)
     if "adni" in which:
         golden_adni(ssm, mmm, uss)
+    if "lg" in which:
+        golden_lg_component(ssm)

@@ -121,3 +121,19 @@ def test_headline_kernel_keeps_uniform_parameter_operands():
     assert eff >= 0.85, out
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
     assert re.search(r"DFMA R\d+, R\d+(\.reuse)?, UR\d+, R", sass), "no uniform-register DFMA operands"
+
+
+def test_lg_component_fit_matches_reference():
+    """framework_extended.StateSpaceLinearGaussian.fit (host numpy restatement) against the
+    reference's fitted parameters (tests/golden/lg_component.npz)."""
+    from mtm_b200.framework_extended import state_space_model_linear_gaussian as ssm_lg
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lg_component.npz"))
+    for tag in ("a0", "a1"):
+        mdl = ssm_lg.StateSpaceLinearGaussian(alpha=float(g[f"{tag}_alpha"])).fit((g[f"{tag}_z"], g[f"{tag}_x"]))
+        for got, key in ((mdl.state_init["mean"], "mean"), (mdl.state_init["cov"], "cov"),
+                         (mdl.state_model["coeff"], "A"), (mdl.state_model["covar"], "G"),
+                         (mdl.measurement_model["coeff"], "H"), (mdl.measurement_model["covar"], "L")):
+            assert np.allclose(got, g[f"{tag}_{key}"], rtol=1e-9, atol=1e-12), (tag, key)
+        back = ssm_lg.StateSpaceLinearGaussian().from_pickle(mdl.to_pickle())
+        assert np.array_equal(back.state_model["coeff"], mdl.state_model["coeff"]) and back.alpha == mdl.alpha

@@ -462,3 +462,15 @@ def test_host_streamed_step_equals_resident_step(eng):
         assert np.array_equal(ah.numpy(), a_res.cpu().numpy())
         assert relerr(ph.numpy(), p_res.cpu().numpy()) < 1e-12
         assert torch.equal(pd.cpu(), ph)
+
+
+def test_lg_component_score():
+    """framework_extended.StateSpaceLinearGaussian.score on the E-step kernel (single cluster) against
+    the reference's score, on the training data and on held-out data with extra missing states."""
+    from mtm_b200.framework_extended import state_space_model_linear_gaussian as ssm_lg
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lg_component.npz"))
+    for tag in ("a0", "a1"):
+        mdl = ssm_lg.StateSpaceLinearGaussian(alpha=float(g[f"{tag}_alpha"])).fit((g[f"{tag}_z"], g[f"{tag}_x"]))
+        assert relerr(mdl.score(), g[f"{tag}_score"]) < RTOL
+        assert relerr(mdl.score((g[f"{tag}_zt"], g[f"{tag}_xt"])), g[f"{tag}_score_t"]) < RTOL

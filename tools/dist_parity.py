@@ -54,6 +54,21 @@ def main():
         if rank == 0:
             print(f"{key:10s} world={world} exit={info['exit']:10s} E-steps={info['n_e_steps']:3d} "
                   f"max rel param err {err:.1e} identical-across-ranks={same} -> {'OK' if good else 'MISMATCH'}")
+    # batched restarts (mtm_sweep_fit) on shards: Q of every restart must equal the reference's objectives
+    gr = np.load(os.path.join(ROOT, "tests", "golden", "restarts.npz"))
+    z, x = gr["B_z"], gr["B_x"]
+    n, T, d, l, n_c, n_starts = (int(v) for v in gr["B_meta"])
+    lo, hi = mdist.shard_bounds(n, world, rank)
+    data = mtm_b200.DeviceData(z[:, lo:hi], x[:, lo:hi], device)
+    a0 = np.stack([np.random.default_rng(100 + i).integers(0, n_c, n)[lo:hi] for i in range(n_starts)]).astype(np.int32)
+    assign = torch.from_numpy(a0).to(device)
+    P, infos, scores, sstat = eng.sweep_fit(data, assign, n_c, 0.0, 100)
+    ref_obj = gr["B_objectives"][1:]  # [0] is the k-means start
+    err = float(np.max(np.abs(scores[:, 0] - ref_obj) / np.abs(ref_obj)))
+    good = err < 1e-9 and all(i["exit"] in ("converged", "guard", "exhausted") for i in infos)
+    ok = ok and good
+    if rank == 0:
+        print(f"sweep      world={world} restarts={n_starts} max rel Q err {err:.1e} -> {'OK' if good else 'MISMATCH'}")
     flag = torch.tensor([1 if ok else 0], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     mdist.detach(eng)
