@@ -4,6 +4,8 @@ golden vectors produced by the unmodified reference (tests/golden) and the CPU o
 Bar (BASELINE.json north_star): cluster assignments, switch counts and iteration counts
 bit-exact; log-likelihoods, parameters, probabilities and scores within 1e-9 relative."""
 
+import os
+
 import numpy as np
 import pytest
 
