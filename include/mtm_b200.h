@@ -211,6 +211,16 @@ int mtm_comm_unique_id(void *id128_out);
 int mtm_comm_init(mtm_handle *h, const void *id128, int world_size, int rank);
 int mtm_comm_destroy(mtm_handle *h);
 
+/* ---- initial assignment on the device --------------------------------------------------------------
+ * Bit-for-bit twin of the reference's random initialisation
+ *     np.random.default_rng(seed).integers(low=0, high=n_c, size=n)          [MMM:128, 166-168]
+ * pcg_state = {state_hi, state_lo, inc_hi, inc_lo}: the 128-bit PCG64 state and increment of the seeded
+ * generator (numpy: np.random.PCG64(seed).state["state"]).  assign_dev (n) int32 out.  Every thread jumps
+ * its own copy of the generator ahead; numpy's rare Lemire rejections (each shifts all later elements by
+ * one draw) are located first and replayed exactly.  Synchronises. */
+int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64_t n, int32_t *assign_dev,
+                      int *n_rejected_host);
+
 /* ---- measurement ---------------------------------------------------------------------------------
  * DFMA-saturating micro-kernel: FP64 peak of this device in TFLOP/s (FMA = 2 flop), best of `reps`,
  * CUDA-event timed.  Denominator of the FP64 roofline (MEASURED_PEAKS.json has none). */

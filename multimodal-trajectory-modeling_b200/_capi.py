@@ -71,6 +71,7 @@ SIGNATURES = {
     "mtm_comm_unique_id": (_i, [_vp]),
     "mtm_comm_init": (_i, [_vp, _vp, _i, _i]),
     "mtm_comm_destroy": (_i, [_vp]),
+    "mtm_random_labels": (_i, [_vp, ctypes.POINTER(ctypes.c_uint64), _i, _i64, _vp, ctypes.POINTER(_i)]),
     "mtm_fp64_peak": (_i, [_vp, _i, ctypes.POINTER(_d)]),
     "mtm_launch_count": (_i64, [_vp]),
 }

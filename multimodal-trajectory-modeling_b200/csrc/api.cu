@@ -827,6 +827,58 @@ int mtm_comm_destroy(mtm_handle *h) {
     return 0;
 }
 
+int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64_t n, int32_t *assign_dev,
+                      int *n_rejected_host) {
+    if (!h || !pcg_state || !assign_dev) return -1;
+    if (n_c < 1 || n < 1) return fail(h, -1, "bad arguments");
+    DeviceGuard g(h->device);
+    constexpr int kCap = 4096;
+    long long *d_list = nullptr;
+    int *d_cnt = nullptr;
+    MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&d_list), sizeof(long long) * kCap + sizeof(int)));
+    d_cnt = reinterpret_cast<int *>(d_list + kCap);
+    unsigned long long st[4] = {pcg_state[0], pcg_state[1], pcg_state[2], pcg_state[3]};
+    long long h_list[kCap];
+    int n_rej = 0;
+    if (n_c > 1) {
+        // The first n + slack draws cover the n accepted ones as long as fewer than `slack` of them are rejected;
+        // widen until that holds (rejections are ~n * n_c / 2^32).
+        long long slack = 64;
+        for (int attempt = 0; attempt < 6; ++attempt) {
+            MTM_CUDA(h, cudaMemsetAsync(d_cnt, 0, sizeof(int), h->stream));
+            MTM_CUDA(h, launch_rng_reject(st, (unsigned int)n_c, n + slack, d_list, kCap, d_cnt, h->stream));
+            h->launches += 1;
+            MTM_CUDA(h, cudaMemcpyAsync(&n_rej, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+            if (n_rej > kCap) {
+                cudaFree(d_list);
+                return fail(h, -1, "more than %d rejected draws: n too large for this n_c", kCap);
+            }
+            if (n_rej < slack) break;
+            slack = 2 * (long long)n_rej + 64;
+        }
+        if (n_rej > 0) {
+            MTM_CUDA(h, cudaMemcpy(h_list, d_list, sizeof(long long) * n_rej, cudaMemcpyDeviceToHost));
+            for (int a = 1; a < n_rej; ++a) {  // insertion sort: a handful of entries
+                const long long v = h_list[a];
+                int b = a - 1;
+                while (b >= 0 && h_list[b] > v) {
+                    h_list[b + 1] = h_list[b];
+                    --b;
+                }
+                h_list[b + 1] = v;
+            }
+            MTM_CUDA(h, cudaMemcpy(d_list, h_list, sizeof(long long) * n_rej, cudaMemcpyHostToDevice));
+        }
+    }
+    MTM_CUDA(h, launch_rng_emit(st, (unsigned int)n_c, n, d_list, n_rej, assign_dev, h->stream));
+    h->launches += 1;
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    MTM_CUDA(h, cudaFree(d_list));
+    if (n_rejected_host) *n_rejected_host = n_rej;
+    return 0;
+}
+
 int mtm_fp64_peak(mtm_handle *h, int reps, double *tflops_out) {
     if (!h || !tflops_out) return -1;
     DeviceGuard g(h->device);

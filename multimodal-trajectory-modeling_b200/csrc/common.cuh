@@ -92,6 +92,11 @@ cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStrea
 cudaError_t launch_counts(const int32_t *assign, int64_t n, int n_c, unsigned long long *counts, cudaStream_t s);
 cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, int R, cudaStream_t s);
 cudaError_t run_fp64_peak(int reps, int sm_count, cudaStream_t s, double *tflops);
+// device twin of numpy's default_rng(seed).integers(0, n_c, n); st = {state_hi, state_lo, inc_hi, inc_lo}
+cudaError_t launch_rng_reject(const unsigned long long st[4], unsigned int n_c, long long n_draws, long long *rej_list,
+                              int rej_cap, int *rej_count, cudaStream_t s);
+cudaError_t launch_rng_emit(const unsigned long long st[4], unsigned int n_c, long long n, const long long *rej_sorted,
+                            int n_rej, int32_t *out, cudaStream_t s);
 
 __host__ __device__ inline int param_stride(int d, int l) { return 1 + d + 3 * d * d + d * l + l * l; }
 // [N | n0, sum z (d), sum zz' (d(d+1)/2) | n1, sum u (2d), sum uu' (d(2d+1)) | n2, sum w (d+l), sum ww' ((d+l)(d+l+1)/2)]

@@ -220,6 +220,20 @@ class Engine:
         ss = np.array(sstat[:], dtype=np.int32) if want_scores else None
         return params, out, sc, ss
 
+    def random_labels(self, seed, n_c, n, out=None):
+        """default_rng(seed).integers(0, n_c, n) generated on the device, bit-identical to numpy
+        (mtm_random_labels).  Returns (int32 device tensor, number of rejected draws replayed)."""
+        self._sync_stream()
+        st = np.random.PCG64(seed).state["state"]
+        m = (1 << 64) - 1
+        arr = (ctypes.c_uint64 * 4)(st["state"] >> 64, st["state"] & m, st["inc"] >> 64, st["inc"] & m)
+        if out is None:
+            out = torch.empty(int(n), dtype=torch.int32, device=self.device)
+        rej = ctypes.c_int(0)
+        self._chk(self.lib.mtm_random_labels(self.h, arr, int(n_c), int(n), ctypes.c_void_p(out.data_ptr()),
+                                             ctypes.byref(rej)))
+        return out, int(rej.value)
+
     def fp64_peak(self, reps=10):
         self._sync_stream()
         out = ctypes.c_double(0.0)

@@ -489,9 +489,16 @@ class MMLinGaussSS_marginalizable:
         """[(status, Q, factory)] for seeds 100 .. 100+n_starts-1 (MMM:1449-1455), fitted together."""
         eng = self.engine
         n, k = self.n_data, self.n_clusters
-        a0 = np.stack([np.random.default_rng(seed=100 + i).integers(low=0, high=k, size=n)
-                       for i in range(n_starts)]).astype(np.int32)
-        assign = torch.from_numpy(a0).to(eng.device)
+        if n >= 200_000:
+            # large data: draw rng.integers(0, k, n) for every seed ON the device (bit-identical to numpy,
+            # mtm_random_labels) instead of n_starts host draws + uploads
+            assign = torch.empty((n_starts, n), dtype=torch.int32, device=eng.device)
+            for i in range(n_starts):
+                eng.random_labels(100 + i, k, n, out=assign[i])
+        else:
+            a0 = np.stack([np.random.default_rng(seed=100 + i).integers(low=0, high=k, size=n)
+                           for i in range(n_starts)]).astype(np.int32)
+            assign = torch.from_numpy(a0).to(eng.device)
         params, infos, scores, sstat = eng.sweep_fit(shared, assign, k, self.alpha, n_steps)
         params_h, assign_h = params.cpu().numpy(), assign.cpu().numpy()
         out = []

@@ -476,3 +476,15 @@ def test_lg_component_score():
         mdl = ssm_lg.StateSpaceLinearGaussian(alpha=float(g[f"{tag}_alpha"])).fit((g[f"{tag}_z"], g[f"{tag}_x"]))
         assert relerr(mdl.score(), g[f"{tag}_score"]) < RTOL
         assert relerr(mdl.score((g[f"{tag}_zt"], g[f"{tag}_xt"])), g[f"{tag}_score_t"]) < RTOL
+
+
+def test_device_random_labels_bit_exact(eng):
+    """mtm_random_labels == np.random.default_rng(seed).integers(0, n_c, n) bit for bit (MMM:166-168),
+    including streams in which numpy's Lemire rejection fires (every later element shifts by one draw)."""
+    for seed, n_c, n in [(42, 4, 1000), (100, 8, 1_000_003), (7, 3, 65), (0, 1, 10), (123, 12, 5_000_000),
+                         (5, 70_000, 20_000_000), (9, 70_000, 129)]:
+        got, n_rej = eng.random_labels(seed, n_c, n)
+        want = np.random.default_rng(seed).integers(low=0, high=n_c, size=n)
+        assert np.array_equal(got.cpu().numpy().astype(np.int64), want), (seed, n_c, n, n_rej)
+        if n_c == 70_000 and n > 1_000_000:
+            assert n_rej > 50  # the rejection path really ran
