@@ -194,7 +194,8 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
     a.score_partials = score_partials;
     a.check_done = check_done;
     a.R = R;
-    const int grid = estep_grid(dt->n, h->sm_count, fused);
+    int grid = estep_grid(dt->n, h->sm_count, fused);
+    if (fused && R > 1 && grid > h->sm_count * 6) grid = h->sm_count * 6;  // R x grid partial blocks: keep it small
     if (grid_out) *grid_out = grid;
     if (fused) {
         const size_t n_vals = (size_t)n_c * stats_stride(dt->d, dt->l);

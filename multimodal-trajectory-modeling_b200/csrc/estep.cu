@@ -13,6 +13,8 @@
 // trajectory is streamed from HBM once per E-step: the n_c-1 later cluster passes of the same
 // thread hit L1/L2.  Parameters (n_c x 85 doubles at d=l=4) sit in shared memory and are read
 // as warp-uniform broadcasts.
+#include <cstdlib>
+
 #include "common.cuh"
 #define MTM_DEFINE_CONST_PARAMS
 #include "filter.cuh"
@@ -229,11 +231,17 @@ size_t estep_smem(int n_c, int T0, int d, int l, bool fused) {
 
 int estep_grid(int64_t n, int sm_count, bool fused) {
     const int64_t tiles = (n + kEThreads - 1) / kEThreads;
-    // Static tile striding (uniform cost per tile).  Plain E-step: enough blocks for every SM to hold
-    // its resident set several times over.  Fused: every block also carries n_c*106 double-double
-    // accumulators that a reduction has to read back, so fewer, longer-lived blocks (6 per SM; the
-    // imbalance of the last wave is then at most one tile in ~90 at 10 M trajectories).
-    const int64_t cap = (int64_t)sm_count * (fused ? 6 : 32);
+    // Static tile striding (uniform cost per tile), blocks = a multiple of the SM count.  Plain E-step:
+    // 32 per SM.  Fused: every block also carries n_c*106 double-double accumulators that a reduction has
+    // to read back, which argues for few blocks — but measured at 10 M x 8 (profiles/r1h_grid_sweep.txt)
+    // 3 / 6 / 12 / 24 / 64 blocks per SM give 23.8 / 23.0 / 22.4 / 22.1 / 22.0 ms: many short-lived blocks
+    // de-phase the statistics epilogues of the co-resident blocks.  24 per SM (48 MB of partials at n_c = 8).
+    int per_sm = fused ? 24 : 32;
+    if (const char *e = getenv(fused ? "MTM_FUSED_BLOCKS_PER_SM" : "MTM_ESTEP_BLOCKS_PER_SM")) {  // tuning knob
+        const int v = atoi(e);
+        if (v > 0) per_sm = v;
+    }
+    const int64_t cap = (int64_t)sm_count * per_sm;
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
