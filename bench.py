@@ -277,11 +277,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     eng = mtm_b200.Engine.get(device)
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device=device)
-        if rank == 0:
-            idt = torch.frombuffer(bytearray(eng.unique_id()), dtype=torch.uint8).to(device)
-        dist.broadcast(idt, 0)
-        eng.comm_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
+        from mtm_b200 import dist as mdist
+
+        mdist.attach(eng)  # library-owned NCCL communicator + peer-memory mailboxes (MTM_B200_ALLREDUCE=nccl|p2p)
 
     n_total = args.n if args.scaling == "strong" else args.n * world
     lo = rank * n_total // world
@@ -451,7 +449,8 @@ def main():
                 "config": {"workload": workload, "n_total": n_total, "n_per_gpu": n_loc,
                            "l2_policy": "inputs (512 B x n per GPU) far larger than the 126 MB L2; no flush needed",
                            "parallelism": f"trajectory shards x{world}, one all-reduce of "
-                                          f"{cfg['n_c'] * eng.stats_stride(args.d, args.l) + 2} doubles per iteration"},
+                                          f"{cfg['n_c'] * eng.stats_stride(args.d, args.l) + 2} doubles per iteration "
+                                          f"({os.environ.get('MTM_B200_ALLREDUCE', 'p2p') if world > 1 else 'none'})"},
                 "em_iters_per_s": 1e3 / ms_step,
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_base, "parity": parity,

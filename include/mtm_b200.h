@@ -49,6 +49,7 @@ extern "C" {
 #define MTM_STATUS_SINGULAR 2    /* an exactly zero pivot: the reference's solve raises "singular" */
 #define MTM_STATUS_EMPTY_FIT 4   /* a regression had no usable rows: lstsq / Ridge raise [MMM:1194,1226] */
 #define MTM_STATUS_CHOL_FAIL 8   /* normal equations not positive definite in the M-step */
+#define MTM_STATUS_COMM_TIMEOUT 16 /* a peer never arrived in the peer-memory all-reduce */
 
 /* exit codes of the EM loop [MMM:1310-1366] */
 #define MTM_EXIT_RUNNING 0
@@ -210,6 +211,14 @@ int mtm_sweep_fit(mtm_handle *h, int n_c, int n_restarts, double alpha, int n_st
 int mtm_comm_unique_id(void *id128_out);
 int mtm_comm_init(mtm_handle *h, const void *id128, int world_size, int rank);
 int mtm_comm_destroy(mtm_handle *h);
+/* Optional, after mtm_comm_init: replace the per-iteration ncclAllReduce of the statistics (6.8 KB at n_c = 8,
+ * latency-bound) by a one-shot all-reduce over NVLink peer memory — every rank stores its vector into every
+ * peer's mailbox (CUDA IPC mapped), then adds the world vectors in rank order (bit-identical on all ranks).
+ *   mtm_p2p_export: allocate this rank's mailbox and return its 64-byte IPC handle;
+ *   mtm_p2p_attach: handles_all = world_size x 64 bytes in rank order (exchanged by the caller).
+ * Exchanges larger than the mailbox (many batched restarts) keep using NCCL. */
+int mtm_p2p_export(mtm_handle *h, void *handle64_out);
+int mtm_p2p_attach(mtm_handle *h, const void *handles_all, int world_size, int rank);
 
 /* ---- initial assignment on the device --------------------------------------------------------------
  * Bit-for-bit twin of the reference's random initialisation

@@ -21,6 +21,7 @@ STATUS_NONFINITE = 1
 STATUS_SINGULAR = 2
 STATUS_EMPTY_FIT = 4
 STATUS_CHOL_FAIL = 8
+STATUS_COMM_TIMEOUT = 16
 
 EXIT_RUNNING, EXIT_CONVERGED, EXIT_GUARD, EXIT_EXHAUSTED, EXIT_GUARD0, EXIT_ERROR = 0, 1, 2, 3, 4, 5
 EXIT_NAMES = {0: "running", 1: "converged", 2: "guard", 3: "exhausted", 4: "guard0", 5: "error"}
@@ -71,6 +72,8 @@ SIGNATURES = {
     "mtm_comm_unique_id": (_i, [_vp]),
     "mtm_comm_init": (_i, [_vp, _vp, _i, _i]),
     "mtm_comm_destroy": (_i, [_vp]),
+    "mtm_p2p_export": (_i, [_vp, _vp]),
+    "mtm_p2p_attach": (_i, [_vp, _vp, _i, _i]),
     "mtm_random_labels": (_i, [_vp, ctypes.POINTER(ctypes.c_uint64), _i, _i64, _vp, ctypes.POINTER(_i)]),
     "mtm_fp64_peak": (_i, [_vp, _i, ctypes.POINTER(_d)]),
     "mtm_launch_count": (_i64, [_vp]),

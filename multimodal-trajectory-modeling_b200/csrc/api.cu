@@ -92,6 +92,13 @@ struct mtm_handle {
     bool stream_ready = false;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
+    // peer-memory all-reduce (p2p.cu)
+    P2PView p2p{};
+    bool p2p_on = false;
+    double *p2p_mailbox = nullptr;   // own mailbox (cudaMalloc, exported through IPC)
+    void *p2p_mapped[kMaxPeers] = {};  // peers' mailboxes opened here
+    unsigned int *p2p_counter = nullptr;
+    unsigned int p2p_seq = 0;
     std::string err;
     int64_t launches = 0;
 };
@@ -227,8 +234,16 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
     return 0;
 }
 
+constexpr int kP2PCap = 16384;  // doubles per rank and parity in a mailbox (128 KB): n_c * 106 + 2 fits for n_c <= 64
+
 int allreduce_stats(mtm_handle *h, double *buf, size_t count) {
     if (!h->comm) return 0;
+    if (h->p2p_on && count <= (size_t)kP2PCap) {
+        h->p2p_seq += 1;
+        MTM_CUDA(h, launch_p2p_allreduce(buf, (int)count, h->p2p, h->p2p_seq, h->p2p_counter, h->d_ctrl, h->stream));
+        h->launches += 2;
+        return 0;
+    }
     const int r = g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
     if (r != 0) return fail(h, -3, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
     return 0;
@@ -815,8 +830,62 @@ int mtm_comm_init(mtm_handle *h, const void *id128, int world_size, int rank) {
     return 0;
 }
 
+int mtm_p2p_export(mtm_handle *h, void *handle64_out) {
+    if (!h || !handle64_out) return -1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(h->device);
+    if (!h->p2p_mailbox) {
+        const size_t bytes = (size_t)2 * kMaxPeers * kP2PCap * sizeof(double) + 2 * kMaxPeers * sizeof(unsigned int);
+        MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->p2p_mailbox), bytes));
+        MTM_CUDA(h, cudaMemset(h->p2p_mailbox, 0, bytes));
+        MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->p2p_counter), sizeof(unsigned int)));
+        MTM_CUDA(h, cudaMemset(h->p2p_counter, 0, sizeof(unsigned int)));
+    }
+    cudaIpcMemHandle_t ipc;
+    MTM_CUDA(h, cudaIpcGetMemHandle(&ipc, h->p2p_mailbox));
+    memcpy(handle64_out, &ipc, sizeof(ipc));
+    return 0;
+}
+
+int mtm_p2p_attach(mtm_handle *h, const void *handles_all, int world_size, int rank) {
+    if (!h || !handles_all) return -1;
+    if (!h->p2p_mailbox) return fail(h, -1, "call mtm_p2p_export first");
+    if (world_size < 2 || world_size > kMaxPeers) return fail(h, -1, "world size %d outside [2, %d]", world_size, kMaxPeers);
+    DeviceGuard g(h->device);
+    const size_t data_doubles = (size_t)2 * kMaxPeers * kP2PCap;
+    for (int q = 0; q < world_size; ++q) {
+        void *base = nullptr;
+        if (q == rank) {
+            base = h->p2p_mailbox;
+        } else {
+            cudaIpcMemHandle_t ipc;
+            memcpy(&ipc, static_cast<const char *>(handles_all) + (size_t)q * 64, sizeof(ipc));
+            MTM_CUDA(h, cudaIpcOpenMemHandle(&base, ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->p2p_mapped[q] = base;
+        }
+        h->p2p.data[q] = static_cast<double *>(base);
+        h->p2p.flags[q] = reinterpret_cast<unsigned int *>(static_cast<double *>(base) + data_doubles);
+    }
+    h->p2p.world = world_size;
+    h->p2p.rank = rank;
+    h->p2p.cap = kP2PCap;
+    h->p2p_seq = 0;
+    h->p2p_on = true;
+    return 0;
+}
+
 int mtm_comm_destroy(mtm_handle *h) {
     if (!h) return -1;
+    if (h->p2p_on) {
+        DeviceGuard g(h->device);
+        cudaStreamSynchronize(h->stream);
+        for (int q = 0; q < kMaxPeers; ++q)
+            if (h->p2p_mapped[q]) {
+                cudaIpcCloseMemHandle(h->p2p_mapped[q]);
+                h->p2p_mapped[q] = nullptr;
+            }
+        h->p2p_on = false;
+    }
     if (h->comm && g_nccl.ok) {
         DeviceGuard g(h->device);
         cudaStreamSynchronize(h->stream);

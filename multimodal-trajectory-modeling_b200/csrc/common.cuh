@@ -73,6 +73,16 @@ struct FinalizeArgs {
     int R;                   // batched restarts: one block per restart; stats (R, n_vals + 2), params (R, n_c, pstride)
 };
 
+// peer-memory mailboxes of the one-shot all-reduce (p2p.cu); at most 16 ranks (one NVSwitch box)
+constexpr int kMaxPeers = 16;
+struct P2PView {
+    double *data[kMaxPeers];         // data[q]: rank q's mailbox, mapped here: [2][world][cap] doubles
+    unsigned int *flags[kMaxPeers];  // flags[q]: rank q's flags: [2][world]
+    int world, rank, cap;
+};
+cudaError_t launch_p2p_allreduce(double *buf, int count, const P2PView &v, unsigned int seq, unsigned int *done_counter,
+                                 Ctrl *ctrl, cudaStream_t s);
+
 // launchers (one translation unit per kernel family so that nvcc can build them in parallel)
 cudaError_t launch_estep(const EStepArgs &a, int grid, size_t smem, cudaStream_t s);
 int estep_grid(int64_t n, int sm_count, bool fused);

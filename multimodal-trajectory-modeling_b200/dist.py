@@ -4,6 +4,8 @@ library (mtm_em_fit / mtm_mstep / mtm_score) on its own NCCL communicator."""
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as tdist
@@ -35,6 +37,12 @@ def attach(engine, group=None) -> None:
     payload = [engine.unique_id() if rank == 0 else None]
     tdist.broadcast_object_list(payload, src=0, group=group)
     engine.comm_init(payload[0], world, rank)
+    # The per-iteration exchange (6.8 KB at n_c = 8) is latency-bound: use the one-shot all-reduce over NVLink
+    # peer memory unless MTM_B200_ALLREDUCE=nccl.  The 64-byte IPC handles travel through torch.distributed.
+    if os.environ.get("MTM_B200_ALLREDUCE", "p2p").lower() != "nccl" and world <= 16:
+        handles = [None] * world
+        tdist.all_gather_object(handles, engine.p2p_export(), group=group)
+        engine.p2p_attach(handles, world, rank)
 
 
 def detach(engine) -> None:

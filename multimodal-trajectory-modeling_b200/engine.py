@@ -251,6 +251,16 @@ class Engine:
         self._chk(self.lib.mtm_comm_init(self.h, buf, world, rank))
         self.world, self.rank = world, rank
 
+    def p2p_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._chk(self.lib.mtm_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_attach(self, handles, world: int, rank: int):
+        blob = b"".join(handles)
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        self._chk(self.lib.mtm_p2p_attach(self.h, buf, world, rank))
+
     def comm_destroy(self):
         self._chk(self.lib.mtm_comm_destroy(self.h))
         self.world, self.rank = 1, 0

@@ -32,6 +32,8 @@ home_dir = os.environ.get("MTM_B200_HOME", os.path.dirname(os.path.dirname(os.pa
 
 def _raise_for_status(status: int, alpha: float = 0.0):
     """Re-raise what the reference raises for the same numerical condition."""
+    if status & C.STATUS_COMM_TIMEOUT:
+        raise C.MtmError("peer-memory all-reduce timed out: a rank did not arrive")
     if status & C.STATUS_NONFINITE:
         # numba's det/solve on a covariance block holding NaN/inf (SSM:771-773)
         raise np.linalg.LinAlgError("Array must not contain infs or NaNs.")
