@@ -228,7 +228,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000, help="total trajectories (config C3: 10 M)")
+    ap.add_argument("--trajectories", "--n", dest="n", type=int, default=10_000_000,
+                    help="total trajectories (config C3: 10 M); use --trajectories under torchrun (its parser grabs --n)")
     ap.add_argument("--n-clusters", type=int, default=8)
     ap.add_argument("--T", type=int, default=8)
     ap.add_argument("--d", type=int, default=4)
