@@ -1,4 +1,6 @@
 #!/bin/bash
-for g in 24 32 48 64 96; do
-  MTM_FUSED_BLOCKS_PER_SM=$g python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('blocks/SM', $g, 'ms', round(d['ms_per_step'],3), 'frac', round(d['roofline']['frac'],4))"
+# usage: tools/grid_sweep.sh <trajectories> <blocks-per-SM list...>
+N=$1; shift
+for g in "$@"; do
+  MTM_FUSED_BLOCKS_PER_SM=$g python bench.py --steps 20 --warmup 3 --trajectories $N --no-e2e --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('n', $N, 'blocks/SM', $g, 'ms', round(d['ms_per_step'],4), 'kernel', round(d['roofline']['kernel_ms'],4), 'frac', round(d['roofline']['frac'],4))"
 done
