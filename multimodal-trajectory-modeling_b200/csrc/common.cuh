@@ -42,7 +42,7 @@ struct EStepArgs {
     int R;                         // batched restarts: gridDim.y independent fits (0/1 = single fit); arrays
                                    // params (R, n_c, stride), assign (R, n), ctrl [R], counts (R, MAX_CLUSTERS),
                                    // score_partials (R, grid, 2), stats_partials (R, grid, n_c, sstride, 2)
-    int tshift;                    // always 0 (see filter_eval): keeps the parameter loads inside the time loop
+    int tshift;                    // always 0 (see filter_eval): a never-taken uniform branch that fixes the code shape
     double *stats_partials;        // nullable: fused mode — the M-step statistics of the NEW labels are
                                    // accumulated in the same pass: (grid, n_c, sstride, 2) block sums
 };

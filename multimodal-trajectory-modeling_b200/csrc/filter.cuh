@@ -387,11 +387,11 @@ __device__ __forceinline__ void load_row(const double *__restrict__ p, double (&
 
 // One full evaluation.  z_i / x_i point at step 0 of trajectory i; zs / xs = step strides in doubles.
 // fin[t] = bit mask of finite unconditional means at step t: bits [0, d) for z, [16, 16 + l) for x.
-// `tshift` is a kernel argument that is ZERO at run time.  The parameter offsets of step t are formed as
-// base + t * tshift: still warp-uniform (so the loads go through the uniform datapath, LDCU -> UR
-// operands), but formally dependent on t, which keeps ptxas from hoisting the loop-invariant parameter
-// loads out of the time loop into ~100 vector registers (what it does otherwise whenever it finds the
-// registers, and what costs the register-file read bandwidth the DFMA stream needs).
+// `tshift` is a kernel argument that is ZERO at run time.  Its only use: in the observation-only
+// instantiation (HAS_Z = false) the hidden-state code stays in the kernel behind `tshift != 0`, a
+// warp-uniform branch that is never taken.  With the same code shape as the joint kernel ptxas 12.9 keeps the
+// uniform-datapath parameter operands there too (modelled FP64-pipe efficiency 0.89 instead of 0.80,
+// tools/sass_reuse.py); the null z pointer is never dereferenced.
 template <class DM, bool HAS_Z, class PS>
 __device__ __forceinline__ double filter_eval(const DM &dm, const double *__restrict__ z_i, int64_t zs,
                                               const double *__restrict__ x_i, int64_t xs, int T0,
@@ -402,20 +402,19 @@ __device__ __forceinline__ double filter_eval(const DM &dm, const double *__rest
         filter_init(dm, f, p0);
     }
     double zt[DM::DM], xt[DM::LM];
-    if (HAS_Z) load_row<DM::DM>(z_i, zt, dm.d(), DM::kStatic);
+    if (HAS_Z || tshift != 0) load_row<DM::DM>(z_i, zt, dm.d(), DM::kStatic);
     load_row<DM::LM>(x_i, xt, dm.l(), DM::kStatic);
-    (void)tshift;
     const ParamView<DM, PS> p(dm, psrc);
     for (int t = 0; t < T0; ++t) {
         // software pipeline: issue the loads of step t+1 before the arithmetic of step t
         double zn[DM::DM], xn[DM::LM];
         const bool last = (t + 1 == T0);  // warp-uniform
         const int tn = last ? t : t + 1;
-        if (HAS_Z) load_row<DM::DM>(z_i + (int64_t)tn * zs, zn, dm.d(), DM::kStatic);
+        if (HAS_Z || tshift != 0) load_row<DM::DM>(z_i + (int64_t)tn * zs, zn, dm.d(), DM::kStatic);
         load_row<DM::LM>(x_i + (int64_t)tn * xs, xn, dm.l(), DM::kStatic);
         const uint32_t fm = fin[t];
         if (t > 0) filter_propagate(dm, f, p);
-        if (HAS_Z) filter_condition_z(dm, f, zt, fm & 0xffffu);
+        if (HAS_Z || tshift != 0) filter_condition_z(dm, f, zt, fm & 0xffffu);
         filter_condition_x(dm, f, p, xt, fm >> 16, last);
         filter_rescale(f);
         MTM_UNROLL
