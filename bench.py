@@ -439,7 +439,7 @@ def main():
                        "parameters are downloaded"}
 
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
         b = run_cpu_arm(args, cfg, steps=1, warmup=0)
         cpu_base = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
 

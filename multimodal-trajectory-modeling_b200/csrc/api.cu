@@ -906,6 +906,10 @@ int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64
     long long *d_list = nullptr;
     int *d_cnt = nullptr;
     MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&d_list), sizeof(long long) * kCap + sizeof(int)));
+    struct Free {  // scratch is released on every exit path
+        void *p;
+        ~Free() { cudaFree(p); }
+    } free_list{d_list};
     d_cnt = reinterpret_cast<int *>(d_list + kCap);
     unsigned long long st[4] = {pcg_state[0], pcg_state[1], pcg_state[2], pcg_state[3]};
     long long h_list[kCap];
@@ -920,10 +924,7 @@ int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64
             h->launches += 1;
             MTM_CUDA(h, cudaMemcpyAsync(&n_rej, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             MTM_CUDA(h, cudaStreamSynchronize(h->stream));
-            if (n_rej > kCap) {
-                cudaFree(d_list);
-                return fail(h, -1, "more than %d rejected draws: n too large for this n_c", kCap);
-            }
+            if (n_rej > kCap) return fail(h, -1, "more than %d rejected draws: n too large for this n_c", kCap);
             if (n_rej < slack) break;
             slack = 2 * (long long)n_rej + 64;
         }
@@ -944,7 +945,6 @@ int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64
     MTM_CUDA(h, launch_rng_emit(st, (unsigned int)n_c, n, d_list, n_rej, assign_dev, h->stream));
     h->launches += 1;
     MTM_CUDA(h, cudaStreamSynchronize(h->stream));
-    MTM_CUDA(h, cudaFree(d_list));
     if (n_rejected_host) *n_rejected_host = n_rej;
     return 0;
 }

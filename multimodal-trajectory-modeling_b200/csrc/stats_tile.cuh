@@ -97,7 +97,7 @@ __device__ __forceinline__ void reduce_by_cluster(const double *feat, int F, dou
 struct StatsSmem {
     double *acc;   // n_c * sstride * 2 (hi, lo)
     double *feat;  // FMAX * (kSThreads + 1)
-    int *list;     // kSThreads
+    int *list;     // kSThreads (unused since the features are staged in sorted order; keeps the layout)
     int *start;    // n_c + 1
     int *wcnt;     // warps * n_c
     __device__ __forceinline__ void carve(unsigned char *base, int n_c, int d, int l) {
