@@ -174,7 +174,8 @@ int ensure_ctrl(mtm_handle *h, int R) {
 }
 
 bool can_fuse(const mtm_data *dt, int n_c) {
-    return dt->z_dev != nullptr && estep_smem(n_c, dt->T, dt->d, dt->l, true) <= 72 * 1024;
+    // up to 110 KB of shared memory per block (2 blocks/SM) the fused kernel still beats a separate statistics pass
+    return dt->z_dev != nullptr && estep_smem(n_c, dt->T, dt->d, dt->l, true) <= 110 * 1024;
 }
 
 int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n_c, int T0, int32_t *assign,

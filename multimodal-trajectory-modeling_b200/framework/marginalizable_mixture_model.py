@@ -92,13 +92,7 @@ class MMLinGaussSS_marginalizable:
 
         self._correspondence = dict(zip(range(k), string.ascii_uppercase))
         self.inverse_correspondence = {v: c for c, v in self._correspondence.items()}
-        self.hex_hash = hashlib.md5(
-            self.states.tobytes()
-            + self.observations.tobytes()
-            + str(self.n_clusters).encode("utf-8")
-            + (np.format_float_positional(self.alpha, unique=True).encode("utf-8")
-               if self.alpha > 2 * np_eps else b"")
-        ).hexdigest()  # MMM:177-188
+        self._hex_hash = None  # md5 over all data bytes (MMM:177-188): computed on first use, see hex_hash
         self.time_stamp = (datetime.datetime.now(datetime.timezone.utc).replace(microsecond=0)
                            .astimezone().isoformat())
         self.last_trained = None
@@ -136,6 +130,25 @@ class MMLinGaussSS_marginalizable:
                     + list(self.transition_matrices) + list(self.measurement_matrices))
                 + sum(tri(x) for x in list(self.init_state_covs) + list(self.transition_covs)
                       + list(self.measurement_covs)))
+
+    @property
+    def hex_hash(self) -> str:
+        """md5 of states bytes + observations bytes + n_clusters (+ alpha), the reference's cache key
+        (MMM:177-188).  Same value as the reference; evaluated lazily because hashing a 10 M-trajectory data
+        set costs seconds and only the pickle cache needs it."""
+        if self._hex_hash is None:
+            md5 = hashlib.md5()
+            md5.update(np.ascontiguousarray(self.states).data)
+            md5.update(np.ascontiguousarray(self.observations).data)
+            md5.update(str(self.n_clusters).encode("utf-8"))
+            if self.alpha > 2 * np_eps:
+                md5.update(np.format_float_positional(self.alpha, unique=True).encode("utf-8"))
+            self._hex_hash = md5.hexdigest()
+        return self._hex_hash
+
+    @hex_hash.setter
+    def hex_hash(self, value: str) -> None:
+        self._hex_hash = value
 
     @property
     def correspondence(self) -> dict:

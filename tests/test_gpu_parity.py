@@ -488,3 +488,21 @@ def test_device_random_labels_bit_exact(eng):
         assert np.array_equal(got.cpu().numpy().astype(np.int64), want), (seed, n_c, n, n_rej)
         if n_c == 70_000 and n > 1_000_000:
             assert n_rej > 50  # the rejection path really ran
+
+
+@pytest.mark.parametrize("n_c", [12, 24])
+def test_many_clusters_vs_oracle(mix, n_c):
+    """n_c = 12 (fused kernel at two blocks per SM) and n_c = 24 (statistics too large to fuse: separate
+    pass) against the oracle: same switch sequence, labels and parameters."""
+    from oracle import cport as oc
+    from oracle import dense as od
+
+    n, T, d, l = 40_000, 5, 4, 4
+    z, x = _synthetic(n, T, d, l, n_c, seed=n_c, sep=0.6)
+    a0 = od.random_init(n, n_c, 3)
+    ref = od.train(z, x, a0, n_c, alpha=0.0, n_steps=3, e_step_fn=oc.e_step_seq)
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=n_c, states=z, observations=x, random_seed=3)
+    mdl.train(n_steps=3)
+    assert mdl.fit_info["switches"] == ref.switches
+    assert np.array_equal(mdl.cluster_assignment, ref.assign)
+    assert relerr(mdl._packed_params(), ref.params.packed()) < RTOL
