@@ -22,8 +22,21 @@ import string
 import numpy as np
 import torch
 
-from .. import _capi as C
-from ..engine import DeviceData, Engine
+try:
+    from .. import _capi as C
+    from ..engine import DeviceData, Engine
+except ImportError:
+    # Imported as the TOP-LEVEL package `framework` (the package directory was put first on sys.path so that
+    # the reference's `from framework import marginalizable_mixture_model as mixmodel` resolves here,
+    # INTEGRATION.md section 1): reach the rest of the package through its importable alias.
+    import sys as _sys
+
+    _root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    if _root not in _sys.path:
+        _sys.path.insert(0, _root)
+    import mtm_b200 as _pkg  # noqa: F401
+    from mtm_b200 import _capi as C
+    from mtm_b200.engine import DeviceData, Engine
 
 np_eps = np.finfo(float).eps
 # reference: <repo>/tmp (MMM:36, 229).  Configurable because a package directory may be read-only.

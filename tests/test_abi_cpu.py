@@ -137,3 +137,20 @@ def test_lg_component_fit_matches_reference():
             assert np.allclose(got, g[f"{tag}_{key}"], rtol=1e-9, atol=1e-12), (tag, key)
         back = ssm_lg.StateSpaceLinearGaussian().from_pickle(mdl.to_pickle())
         assert np.array_equal(back.state_model["coeff"], mdl.state_model["coeff"]) and back.alpha == mdl.alpha
+
+
+def test_import_as_reference_package_name():
+    """with the package directory first on sys.path the reference's own import line
+    `from framework import marginalizable_mixture_model as mixmodel` resolves to the drop-in class."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); "
+        "from framework import marginalizable_mixture_model as mixmodel; "
+        "m = mixmodel.MMLinGaussSS_marginalizable(n_clusters=2, states=np.zeros((3, 12, 2)), observations=np.zeros((3, 12, 1))); "
+        "print(type(m).__module__, m.cluster_assignment.shape, len(m.hex_hash))"
+    ) % os.path.join(ROOT, "multimodal-trajectory-modeling_b200")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0, out.stderr[-800:]
+    assert out.stdout.split()[0] == "framework.marginalizable_mixture_model" and "(12,)" in out.stdout
