@@ -370,7 +370,7 @@ def main():
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-                # (profiles/r1d_fused_ncu_summary.md: 1.0373 GB + 23.5 MB for 2 M trajectories = 530.4 B per
+                # (profiles/r1j_fused_ncu_summary.md: 1.0373 GB + 23.5 MB for 2 M trajectories = 530.4 B per
                 # trajectory), scaled to this launch's trajectory count
                 "traffic": 530.4 * n_loc, "traffic_unit": "bytes per launch (ncu-measured 530.4 B/trajectory x n)",
                 "kernel": "estep_kernel<4,4,HAS_Z,CONSTP,FUSE> (E-step + fused M-step statistics; the timed span also "

@@ -93,7 +93,7 @@ int stats_grid(int64_t n, int sm_count);
 size_t stats_smem(int n_c, int d, int l);
 // out (n_vals + 2): reduced statistics, then [n_switches of the preceding E-step, local n].
 // `scratch` holds kReduceSlices * n_vals * 2 doubles (two-stage fixed-order reduction).
-constexpr int kReduceSlices = 16;
+constexpr int kReduceSlices = 64;
 cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
                                 const Ctrl *ctrl, int check_done, int with_switches, double n_local, int R,
                                 cudaStream_t s);

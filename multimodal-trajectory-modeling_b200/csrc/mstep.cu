@@ -65,8 +65,23 @@ __global__ void stats_reduce1_kernel(const double *__restrict__ partials_all, in
     const int s = blockIdx.y, S = gridDim.y;
     if (v >= n_vals) return;
     double hi = 0.0, lo = 0.0;
-    for (int b = s; b < grid; b += S) {
-        const double2 p = *reinterpret_cast<const double2 *>(partials + 2 * ((size_t)b * n_vals + v));
+    int b = s;
+    for (; b + 3 * S < grid; b += 4 * S) {  // four independent loads in flight, added in block order
+        const double2 p0 = __ldcs(reinterpret_cast<const double2 *>(partials + 2 * ((size_t)b * n_vals + v)));
+        const double2 p1 = __ldcs(reinterpret_cast<const double2 *>(partials + 2 * ((size_t)(b + S) * n_vals + v)));
+        const double2 p2 = __ldcs(reinterpret_cast<const double2 *>(partials + 2 * ((size_t)(b + 2 * S) * n_vals + v)));
+        const double2 p3 = __ldcs(reinterpret_cast<const double2 *>(partials + 2 * ((size_t)(b + 3 * S) * n_vals + v)));
+        dd_add(hi, lo, p0.x);
+        lo += p0.y;
+        dd_add(hi, lo, p1.x);
+        lo += p1.y;
+        dd_add(hi, lo, p2.x);
+        lo += p2.y;
+        dd_add(hi, lo, p3.x);
+        lo += p3.y;
+    }
+    for (; b < grid; b += S) {
+        const double2 p = __ldcs(reinterpret_cast<const double2 *>(partials + 2 * ((size_t)b * n_vals + v)));
         dd_add(hi, lo, p.x);
         lo += p.y;
     }
