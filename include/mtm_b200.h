@@ -230,6 +230,27 @@ int mtm_p2p_attach(mtm_handle *h, const void *handles_all, int world_size, int r
 int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64_t n, int32_t *assign_dev,
                       int *n_rejected_host);
 
+/* ---- pattern-ordered residency --------------------------------------------------------------------
+ * The reference keeps trajectories in the caller's order (MMM:75-81).  For a resident training set the
+ * E-step is faster when every aligned group of 32 trajectories shares its per-step "all hidden-state
+ * coordinates present" pattern: whenever all of z_t is present the filtered state is a point mass and a
+ * warp that agrees on it skips the covariance arithmetic of that step (bit-identical results).
+ * mtm_pattern_order: perm_dev (n) int64 out — a stable sort of the trajectories by that pattern (bit t of
+ *   the key, t < min(T, 8): all d coordinates of z[t, i, :] finite); perm[p] = index, in the caller's
+ *   order, of the trajectory to store at resident position p.  A pure function of the data.  Synchronises.
+ * mtm_permute_f64 / _i32: apply it to a (rows, n, w) array (w = 1 for _i32):
+ *   inverse == 0:  dst[r, p, :] = src[r, perm[p], :]   (caller's order -> resident order)
+ *   inverse != 0:  dst[r, perm[p], :] = src[r, p, :]   (resident order -> caller's order)
+ *   e.g. z (T, n, d): rows = T, w = d;  labels (n): rows = 1;  ll / probs (n_c, n): rows = n_c, w = 1.
+ *   Out of place only.  Enqueued on the handle's stream.
+ * Every other entry point is order-agnostic: it works on whatever order the bound data and the label
+ * array share. */
+int mtm_pattern_order(mtm_handle *h, const mtm_data *data, int64_t *perm_dev);
+int mtm_permute_f64(mtm_handle *h, const double *src_dev, double *dst_dev, int64_t rows, int64_t n, int w,
+                    const int64_t *perm_dev, int inverse);
+int mtm_permute_i32(mtm_handle *h, const int32_t *src_dev, int32_t *dst_dev, int64_t rows, int64_t n,
+                    const int64_t *perm_dev, int inverse);
+
 /* ---- measurement ---------------------------------------------------------------------------------
  * DFMA-saturating micro-kernel: FP64 peak of this device in TFLOP/s (FMA = 2 flop), best of `reps`,
  * CUDA-event timed.  Denominator of the FP64 roofline (MEASURED_PEAKS.json has none). */

@@ -950,6 +950,48 @@ int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64
     return 0;
 }
 
+int mtm_pattern_order(mtm_handle *h, const mtm_data *data, int64_t *perm_dev) {
+    if (!h || !data || !perm_dev) return -1;
+    if (!data->z_dev) return fail(h, -1, "mtm_pattern_order needs hidden states (z_dev)");
+    if (data->n < 1 || data->T < 1 || data->d < 1 || data->d > MTM_MAX_DIM) return fail(h, -1, "bad data shape");
+    DeviceGuard g(h->device);
+    void *scratch = nullptr;
+    MTM_CUDA(h, cudaMalloc(&scratch, order_scratch_bytes(data->n, h->sm_count)));
+    struct Free {  // scratch is released on every exit path
+        void *p;
+        ~Free() { cudaFree(p); }
+    } free_scratch{scratch};
+    MTM_CUDA(h, launch_pattern_order(data->z_dev, data->n, data->ld > 0 ? data->ld : data->n, data->T, data->d,
+                                     h->sm_count, scratch, perm_dev, h->stream));
+    h->launches += 3;
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));  // the scratch is freed on return
+    return 0;
+}
+
+int mtm_permute_f64(mtm_handle *h, const double *src_dev, double *dst_dev, int64_t rows, int64_t n, int w,
+                    const int64_t *perm_dev, int inverse) {
+    if (!h || !src_dev || !dst_dev || !perm_dev) return -1;
+    if (rows < 0 || n < 0 || w < 1) return fail(h, -1, "bad arguments");
+    if (src_dev == dst_dev) return fail(h, -1, "mtm_permute_f64 does not work in place");
+    if (rows == 0 || n == 0) return 0;
+    DeviceGuard g(h->device);
+    MTM_CUDA(h, launch_permute_f64(src_dev, dst_dev, rows, n, w, perm_dev, inverse, h->stream));
+    h->launches += 1;
+    return 0;
+}
+
+int mtm_permute_i32(mtm_handle *h, const int32_t *src_dev, int32_t *dst_dev, int64_t rows, int64_t n,
+                    const int64_t *perm_dev, int inverse) {
+    if (!h || !src_dev || !dst_dev || !perm_dev) return -1;
+    if (rows < 0 || n < 0) return fail(h, -1, "bad arguments");
+    if (src_dev == dst_dev) return fail(h, -1, "mtm_permute_i32 does not work in place");
+    if (rows == 0 || n == 0) return 0;
+    DeviceGuard g(h->device);
+    MTM_CUDA(h, launch_permute_i32(src_dev, dst_dev, rows, n, perm_dev, inverse, h->stream));
+    h->launches += 1;
+    return 0;
+}
+
 int mtm_fp64_peak(mtm_handle *h, int reps, double *tflops_out) {
     if (!h || !tflops_out) return -1;
     DeviceGuard g(h->device);

@@ -108,6 +108,15 @@ cudaError_t launch_rng_reject(const unsigned long long st[4], unsigned int n_c, 
 cudaError_t launch_rng_emit(const unsigned long long st[4], unsigned int n_c, long long n, const long long *rej_sorted,
                             int n_rej, int32_t *out, cudaStream_t s);
 
+// pattern-ordered residency (order.cu)
+size_t order_scratch_bytes(int64_t n, int sm_count);
+cudaError_t launch_pattern_order(const double *z, int64_t n, int64_t ld, int T, int d, int sm_count, void *scratch,
+                                 int64_t *perm, cudaStream_t s);
+cudaError_t launch_permute_f64(const double *src, double *dst, int64_t rows, int64_t n, int w, const int64_t *perm,
+                               int inverse, cudaStream_t s);
+cudaError_t launch_permute_i32(const int32_t *src, int32_t *dst, int64_t rows, int64_t n, const int64_t *perm,
+                               int inverse, cudaStream_t s);
+
 __host__ __device__ inline int param_stride(int d, int l) { return 1 + d + 3 * d * d + d * l + l * l; }
 // [N | n0, sum z (d), sum zz' (d(d+1)/2) | n1, sum u (2d), sum uu' (d(2d+1)) | n2, sum w (d+l), sum ww' ((d+l)(d+l+1)/2)]
 __host__ __device__ inline int stats_stride(int d, int l) {

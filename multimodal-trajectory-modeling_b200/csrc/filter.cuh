@@ -341,6 +341,92 @@ __device__ __forceinline__ void filter_condition_x(const DM &dm, FilterState<DM>
     }
 }
 
+// ---- point-mass shortcuts ------------------------------------------------------------------------------------
+// When EVERY hidden-state coordinate of a step is present, the posterior of z_t is the point mass at z_t:
+// P is exactly 0 (filter_condition_z zeroes the rows) and mu == z_t.  The generic code would then only move
+// zeros around (C = P H = 0, gains 0, A'PA = 0); these two functions skip that work and give bit-identical
+// numbers.  They are taken on a WARP-UNIFORM vote (all 32 trajectories of the warp), so there is no
+// divergence; storing the resident data sorted by its per-step "z complete" pattern (engine.py) makes the vote
+// succeed for ~41 % of the steps at 20 % element-wise missingness, saving ~26 % of the FP64 work.
+
+// (mu, P) <- (mu A, Gamma): the propagation of a point mass
+template <class DM, class PV>
+__device__ __forceinline__ void filter_propagate_point(const DM &dm, FilterState<DM> &f, const PV &p) {
+    const int d = dm.d();
+    double nmu[DM::DM];
+    MTM_UNROLL
+    for (int j = 0; j < DM::DM; ++j) nmu[j] = 0.0;
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            const double mi = f.mu[i];
+            MTM_UNROLL
+            for (int j = 0; j < DM::DM; ++j)
+                if (j < d) nmu[j] = fma(mi, p.A(i * d + j), nmu[j]);
+        }
+    }
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            f.mu[i] = nmu[i];
+            MTM_UNROLL
+            for (int j = i; j < DM::DM; ++j)
+                if (j < d) f.P[i][j] = p.G(i * d + j);
+        }
+    }
+}
+
+// x_t given a known z_t: mean z_t H, covariance Lambda; only the x-block is conditioned, (mu, P) stay.
+template <class DM, class PV>
+__device__ __forceinline__ void filter_condition_x_point(const DM &dm, FilterState<DM> &f, const PV &p,
+                                                         const double (&xt)[DM::LM], uint32_t finmask) {
+    const int d = dm.d(), l = dm.l();
+    double mux[DM::LM];
+    double Sx[DM::LM][DM::LM];
+    MTM_UNROLL
+    for (int b = 0; b < DM::LM; ++b) mux[b] = 0.0;
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            const double mi = f.mu[i];
+            MTM_UNROLL
+            for (int b = 0; b < DM::LM; ++b)
+                if (b < l) mux[b] = fma(mi, p.H(i * l + b), mux[b]);
+        }
+    }
+    MTM_UNROLL
+    for (int a = 0; a < DM::LM; ++a) {
+        if (a < l) {
+            MTM_UNROLL
+            for (int b = a; b < DM::LM; ++b)
+                if (b < l) Sx[a][b] = p.Lam(a * l + b);
+        }
+    }
+    MTM_UNROLL
+    for (int j = 0; j < DM::LM; ++j) {
+        if (j < l) {
+            const double y = xt[j];
+            const bool obs = finite_bits(y) && ((finmask >> j) & 1u);
+            const double s = Sx[j][j];
+            const double r = obs ? fast_rcp(s) : 0.0;
+            const double v = obs ? (y - mux[j]) : 0.0;
+            f.q = fma(v * v, r, f.q);
+            f.mant *= obs ? s : 1.0;
+            f.k += obs ? 1 : 0;
+            MTM_UNROLL
+            for (int a = j + 1; a < DM::LM; ++a) {
+                if (a < l) {
+                    const double g = Sx[j][a] * r;
+                    mux[a] = fma(g, v, mux[a]);
+                    MTM_UNROLL
+                    for (int b = a; b < DM::LM; ++b)
+                        if (b < l) Sx[a][b] = fma(-g, Sx[j][b], Sx[a][b]);
+                }
+            }
+        }
+    }
+}
+
 // keep the running determinant in range: move the binary exponent of `mant` into `expo`
 template <class DM>
 __device__ __forceinline__ void filter_rescale(FilterState<DM> &f) {
@@ -401,26 +487,62 @@ __device__ __forceinline__ double filter_eval(const DM &dm, const double *__rest
         const ParamView<DM, PS> p0(dm, psrc);
         filter_init(dm, f, p0);
     }
+    // Loads: x_t is requested at the top of its own step (first used after the propagation and the
+    // z-conditioning); z_{t+1} is prefetched at the top of step t into zn and handed over at the loop end.
+    // That hand-over is PINNED to the loop end by a predicate ptxas cannot resolve (always true: the exponent
+    // counter never reaches INT_MAX).  As plain copies ptxas 12.9 hoisted them to right behind the loads to
+    // recycle the registers, so every step stalled for a full memory latency on the first copy (ncu: 7.7 % of
+    // the warp samples of the time loop on one IMAD.MOV, long scoreboard).  Loading z where it is used, or
+    // anywhere but the loop top, makes ptxas drop the uniform-datapath parameter operands (LDCU -> LDC,
+    // tools/sass_loops.py), a far bigger loss.
+    // The observation-only instantiation has no z stream, so there the same pattern is applied to x.
+    constexpr bool XPRE = !HAS_Z;
     double zt[DM::DM], xt[DM::LM];
     if (HAS_Z || tshift != 0) load_row<DM::DM>(z_i, zt, dm.d(), DM::kStatic);
-    load_row<DM::LM>(x_i, xt, dm.l(), DM::kStatic);
+    if (XPRE) load_row<DM::LM>(x_i, xt, dm.l(), DM::kStatic);
     const ParamView<DM, PS> p(dm, psrc);
+    bool p_point = false;  // warp-uniform: the posterior of the previous step is a point mass (P == 0, mu == z)
     for (int t = 0; t < T0; ++t) {
-        // software pipeline: issue the loads of step t+1 before the arithmetic of step t
-        double zn[DM::DM], xn[DM::LM];
         const bool last = (t + 1 == T0);  // warp-uniform
         const int tn = last ? t : t + 1;
+        double zn[DM::DM], xn[DM::LM];
         if (HAS_Z || tshift != 0) load_row<DM::DM>(z_i + (int64_t)tn * zs, zn, dm.d(), DM::kStatic);
-        load_row<DM::LM>(x_i + (int64_t)tn * xs, xn, dm.l(), DM::kStatic);
+        if (XPRE) load_row<DM::LM>(x_i + (int64_t)tn * xs, xn, dm.l(), DM::kStatic);
+        else load_row<DM::LM>(x_i + (int64_t)t * xs, xt, dm.l(), DM::kStatic);
         const uint32_t fm = fin[t];
-        if (t > 0) filter_propagate(dm, f, p);
+        // warp-uniform: are all hidden-state coordinates of this step present for all 32 trajectories?
+        bool z_point = false;
+        if (HAS_Z || tshift != 0) {
+            uint32_t z_all = 1u;
+            MTM_UNROLL
+            for (int j = 0; j < DM::DM; ++j)
+                if (j < dm.d()) z_all &= (finite_bits(zt[j]) ? 1u : 0u) & (fm >> j);
+            z_point = __all_sync(0xffffffffu, z_all != 0u);
+        }
+        if (t > 0) {
+            if (p_point) filter_propagate_point(dm, f, p);
+            else filter_propagate(dm, f, p);
+        }
         if (HAS_Z || tshift != 0) filter_condition_z(dm, f, zt, fm & 0xffffu);
-        filter_condition_x(dm, f, p, xt, fm >> 16, last);
+        if (z_point) filter_condition_x_point(dm, f, p, xt, fm >> 16);
+        else filter_condition_x(dm, f, p, xt, fm >> 16, last);
+        p_point = z_point;
         filter_rescale(f);
-        MTM_UNROLL
-        for (int k = 0; k < DM::DM; ++k) zt[k] = zn[k];
-        MTM_UNROLL
-        for (int k = 0; k < DM::LM; ++k) xt[k] = xn[k];
+#define MTM_PINNED_COPY(dst, src)                                                                   \
+    asm volatile("{ .reg .pred pp; setp.ne.s32 pp, %2, 0x7fffffff; @pp mov.f64 %0, %1; }" \
+                 : "+d"(dst) : "d"(src), "r"(f.expo))
+        if (HAS_Z) {
+            MTM_UNROLL
+            for (int k = 0; k < DM::DM; ++k)
+                if (k < dm.d()) MTM_PINNED_COPY(zt[k], zn[k]);
+        } else {
+            MTM_UNROLL
+            for (int k = 0; k < DM::DM; ++k) zt[k] = zn[k];
+            MTM_UNROLL
+            for (int k = 0; k < DM::LM; ++k)
+                if (k < dm.l()) MTM_PINNED_COPY(xt[k], xn[k]);
+        }
+#undef MTM_PINNED_COPY
     }
     return filter_finish(f, bad);
 }

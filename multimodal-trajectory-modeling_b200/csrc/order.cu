@@ -1,0 +1,163 @@
+// Pattern-ordered residency: a stable counting sort of the trajectories by their per-step "all hidden-state
+// coordinates present" pattern, and the row permutation kernels that apply it.
+//
+// Why: when every coordinate of z_t is present the filtered state is a point mass, and the E-step kernel has a
+// shortcut for that (filter.cuh, "point-mass shortcuts") — but only on a warp-uniform vote, since a per-lane
+// branch would serialise.  In the reference's storage order (framework/marginalizable_mixture_model.py:75-81,
+// trajectories in the caller's order) 32 neighbouring trajectories practically never agree at 20 % element-wise
+// missingness; ordered by the pattern every aligned group of 32 does (except the <= 256 groups that straddle a
+// bucket boundary).  The order is a pure function of the data (stable sort, no atomics on the result), so fits
+// stay reproducible run to run.
+//
+// Key of trajectory i: bit t (t < min(T, 8)) is set iff all d coordinates of z[t, i, :] are finite.
+// Sort: (1) every warp histograms its contiguous chunk of trajectories; (2) one block turns the
+// (bucket-major, warp-minor) table into start offsets; (3) every warp walks its chunk again and hands out
+// positions in trajectory order.  perm[p] = original index of the trajectory at resident position p.
+#include "common.cuh"
+
+namespace mtm {
+
+constexpr int kOThreads = 256;
+constexpr int kOWarps = kOThreads / 32;
+constexpr int kBuckets = 256;
+
+__device__ __forceinline__ bool finite_hi(double y) { return (__double2hiint(y) & 0x7ff00000) != 0x7ff00000; }
+
+__device__ __forceinline__ int pattern_key(const double *__restrict__ z, int64_t ld, int Tk, int d, int64_t i) {
+    int key = 0;
+    for (int t = 0; t < Tk; ++t) {
+        const double *row = z + ((int64_t)t * ld + i) * d;
+        bool all = true;
+        for (int j = 0; j < d; ++j) all = all && finite_hi(__ldg(row + j));
+        key |= all ? (1 << t) : 0;
+    }
+    return key;
+}
+
+// chunk of warp `unit`: [unit * per, min(n, (unit + 1) * per)), per a multiple of 32
+__global__ void __launch_bounds__(kOThreads) order_hist_kernel(const double *__restrict__ z, int64_t n, int64_t ld,
+                                                                int Tk, int d, int64_t per, unsigned char *keys,
+                                                                unsigned int *hist, int units) {
+    __shared__ unsigned int s_cnt[kOWarps][kBuckets];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x * kOWarps + warp;
+    for (int b = lane; b < kBuckets; b += 32) s_cnt[warp][b] = 0;
+    __syncwarp();
+    const int64_t lo = (int64_t)unit * per;
+    const int64_t hi = lo + per < n ? lo + per : n;
+    for (int64_t base = lo; base < hi; base += 32) {
+        const int64_t i = base + lane;
+        const bool valid = i < hi;
+        const int key = valid ? pattern_key(z, ld, Tk, d, i) : kBuckets;
+        if (valid) keys[i] = (unsigned char)key;
+        const unsigned int m = __match_any_sync(0xffffffffu, key);
+        if (valid && (m & ((1u << lane) - 1u)) == 0) s_cnt[warp][key] += __popc(m);
+        __syncwarp();
+    }
+    for (int b = lane; b < kBuckets; b += 32) hist[(size_t)b * units + unit] = s_cnt[warp][b];
+}
+
+// in-place exclusive prefix sum over `count` entries, one block
+__global__ void __launch_bounds__(1024) order_scan_kernel(unsigned int *v, int64_t count) {
+    __shared__ unsigned long long s_sum[1024];
+    const int tid = threadIdx.x;
+    const int64_t seg = (count + 1023) / 1024;
+    const int64_t lo = (int64_t)tid * seg, hi = lo + seg < count ? lo + seg : count;
+    unsigned long long s = 0;
+    for (int64_t k = lo; k < hi; ++k) s += v[k];
+    s_sum[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the segment sums
+        const unsigned long long add = tid >= o ? s_sum[tid - o] : 0;
+        __syncthreads();
+        s_sum[tid] += add;
+        __syncthreads();
+    }
+    unsigned long long run = tid ? s_sum[tid - 1] : 0;
+    for (int64_t k = lo; k < hi; ++k) {
+        const unsigned int c = v[k];
+        v[k] = (unsigned int)run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(kOThreads) order_scatter_kernel(const unsigned char *__restrict__ keys, int64_t n,
+                                                                   int64_t per, const unsigned int *__restrict__ offs,
+                                                                   int units, int64_t *perm) {
+    __shared__ unsigned int s_pos[kOWarps][kBuckets];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x * kOWarps + warp;
+    for (int b = lane; b < kBuckets; b += 32) s_pos[warp][b] = offs[(size_t)b * units + unit];
+    __syncwarp();
+    const int64_t lo = (int64_t)unit * per;
+    const int64_t hi = lo + per < n ? lo + per : n;
+    for (int64_t base = lo; base < hi; base += 32) {
+        const int64_t i = base + lane;
+        const bool valid = i < hi;
+        const int key = valid ? (int)keys[i] : kBuckets;
+        const unsigned int m = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        unsigned int start = 0;
+        if (valid) start = s_pos[warp][key];
+        __syncwarp();
+        if (valid && rank == 0) s_pos[warp][key] = start + __popc(m);
+        __syncwarp();
+        if (valid) perm[start + rank] = i;
+    }
+}
+
+// (rows, n, w) arrays: gather dst[r, p, :] = src[r, perm[p], :]  or scatter dst[r, perm[p], :] = src[r, p, :]
+template <class T>
+__global__ void __launch_bounds__(256) permute_rows_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t rows,
+                                                            int64_t n, int w, const int64_t *__restrict__ perm,
+                                                            int inverse) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int64_t q = perm[p];
+    const int64_t from = inverse ? p : q, to = inverse ? q : p;
+    for (int64_t r = 0; r < rows; ++r) {
+        const T *s = src + (r * n + from) * w;
+        T *o = dst + (r * n + to) * w;
+        if (sizeof(T) == 8 && (w & 1) == 0) {  // 16-byte rows: vector copies (rows are 16-byte aligned when w is even)
+            for (int k = 0; k < w; k += 2)
+                *reinterpret_cast<double2 *>(o + k) = __ldg(reinterpret_cast<const double2 *>(s + k));
+        } else {
+            for (int k = 0; k < w; ++k) o[k] = __ldg(s + k);
+        }
+    }
+}
+
+int order_units(int sm_count) { return sm_count * 4 * kOWarps; }  // warps of the sort grid
+
+size_t order_scratch_bytes(int64_t n, int sm_count) {
+    return (size_t)kBuckets * order_units(sm_count) * sizeof(unsigned int) + (size_t)n + 256;
+}
+
+cudaError_t launch_pattern_order(const double *z, int64_t n, int64_t ld, int T, int d, int sm_count, void *scratch,
+                                 int64_t *perm, cudaStream_t s) {
+    const int units = order_units(sm_count);
+    const int grid = units / kOWarps;
+    unsigned int *hist = static_cast<unsigned int *>(scratch);
+    unsigned char *keys = reinterpret_cast<unsigned char *>(hist + (size_t)kBuckets * units);
+    int64_t per = (n + units - 1) / units;
+    per = (per + 31) / 32 * 32;
+    const int Tk = T < 8 ? T : 8;
+    order_hist_kernel<<<grid, kOThreads, 0, s>>>(z, n, ld, Tk, d, per, keys, hist, units);
+    order_scan_kernel<<<1, 1024, 0, s>>>(hist, (int64_t)kBuckets * units);
+    order_scatter_kernel<<<grid, kOThreads, 0, s>>>(keys, n, per, hist, units, perm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_permute_f64(const double *src, double *dst, int64_t rows, int64_t n, int w, const int64_t *perm,
+                               int inverse, cudaStream_t s) {
+    permute_rows_kernel<double><<<(unsigned int)((n + 255) / 256), 256, 0, s>>>(src, dst, rows, n, w, perm, inverse);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_permute_i32(const int32_t *src, int32_t *dst, int64_t rows, int64_t n, const int64_t *perm,
+                               int inverse, cudaStream_t s) {
+    permute_rows_kernel<int32_t><<<(unsigned int)((n + 255) / 256), 256, 0, s>>>(src, dst, rows, n, 1, perm, inverse);
+    return cudaGetLastError();
+}
+
+}  // namespace mtm

@@ -12,9 +12,17 @@ from . import _capi as C
 
 
 class DeviceData:
-    """A data set resident in HBM: z (T, n, d) or None, x (T, n, l), float64, contiguous."""
+    """A data set resident in HBM: z (T, n, d) or None, x (T, n, l), float64, contiguous.
 
-    def __init__(self, states, observations, device):
+    ``pattern_order=True`` stores the trajectories in *resident order*: grouped by their per-step "all
+    hidden-state coordinates present" pattern (``mtm_pattern_order``), which lets whole warps of the E-step take
+    the point-mass shortcut.  ``perm[p]`` is then the caller's index of the trajectory at resident position p;
+    every engine call works in resident order, ``to_resident`` / ``from_resident`` translate label vectors and
+    (rows, n) result matrices at the boundary.  With ``perm is None`` both orders coincide."""
+
+    perm = None
+
+    def __init__(self, states, observations, device, pattern_order=False):
         def up(a):
             if a is None:
                 return None
@@ -36,6 +44,51 @@ class DeviceData:
             self.d = int(self.z.shape[2])
         else:
             self.d = None
+        if pattern_order and self.z is not None and self.n > 1:
+            self._order(device)
+
+    def _order(self, device):
+        eng = Engine.get(device)
+        eng._sync_stream()
+        perm = torch.empty(self.n, dtype=torch.int64, device=self.z.device)
+        st = self.struct()
+        eng._chk(eng.lib.mtm_pattern_order(eng.h, ctypes.byref(st), ctypes.c_void_p(perm.data_ptr())))
+        for name, w in (("z", self.d), ("x", self.l)):
+            src = getattr(self, name)
+            dst = torch.empty_like(src)
+            eng._chk(eng.lib.mtm_permute_f64(eng.h, ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()),
+                                             self.T, self.n, w, ctypes.c_void_p(perm.data_ptr()), 0))
+            setattr(self, name, dst)
+            del src  # stream-ordered: the caching allocator reuses the block only after the copy
+        self.perm = perm
+
+    def to_resident(self, a, dtype=torch.int32):
+        """(n,) or (rows, n) array in the caller's order -> device tensor in resident order."""
+        dev = self.x.device
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        t = t.to(device=dev, dtype=dtype).contiguous()
+        return t if self.perm is None else self._permute(t, inverse=0)
+
+    def from_resident(self, t):
+        """device tensor (n,) or (rows, n) in resident order -> device tensor in the caller's order."""
+        if self.perm is None or t is None:
+            return t
+        return self._permute(t.contiguous(), inverse=1)
+
+    def _permute(self, t, inverse):
+        eng = Engine.get(t.device)
+        eng._sync_stream()
+        rows = 1 if t.dim() == 1 else int(t.shape[0])
+        assert int(t.shape[-1]) == self.n and t.dim() <= 2
+        out = torch.empty_like(t)
+        p = lambda v: ctypes.c_void_p(v.data_ptr())
+        if t.dtype == torch.int32:
+            eng._chk(eng.lib.mtm_permute_i32(eng.h, p(t), p(out), rows, self.n, p(self.perm), inverse))
+        elif t.dtype == torch.float64:
+            eng._chk(eng.lib.mtm_permute_f64(eng.h, p(t), p(out), rows, self.n, 1, p(self.perm), inverse))
+        else:
+            raise TypeError(f"unsupported dtype {t.dtype}")
+        return out
 
     def struct(self, d=None):
         s = C.MtmData()

@@ -179,7 +179,9 @@ class MMLinGaussSS_marginalizable:
 
     def _train_data(self) -> DeviceData:
         if self._data is None:
-            self._data = DeviceData(self.states, self.observations, self.engine.device)
+            # resident order = grouped by the per-step "z complete" pattern (engine.DeviceData); everything
+            # that leaves this class is translated back to the caller's order
+            self._data = DeviceData(self.states, self.observations, self.engine.device, pattern_order=True)
         return self._data
 
     def _packed_params(self) -> np.ndarray:
@@ -218,7 +220,11 @@ class MMLinGaussSS_marginalizable:
         self.measurement_covs = take((l, l))
 
     def _assign_dev(self):
-        return torch.from_numpy(np.ascontiguousarray(self.cluster_assignment, dtype=np.int32)).to(self.engine.device)
+        """Current labels as an int32 device tensor in the training set's resident order."""
+        return self._train_data().to_resident(np.ascontiguousarray(self.cluster_assignment, dtype=np.int32))
+
+    def _assign_host(self, assign_dev) -> np.ndarray:
+        return self._train_data().from_resident(assign_dev).cpu().numpy().astype(np.int64)
 
     def _resolve(self, states, observations):
         """The reference's data-override rule: if `states` is None BOTH come from the training
@@ -234,6 +240,8 @@ class MMLinGaussSS_marginalizable:
         res = self.engine.estep(data, self._packed_params(), self.n_clusters, T0, want_ll=ll, want_probs=probs,
                                 want_prenorm=prenorm, d=d)
         _raise_for_status(res["status"], self.alpha)
+        for k in ("assign", "ll", "probs", "prenorm"):  # resident order -> caller's order
+            res[k] = data.from_resident(res[k])
         return res
 
     def conditional_log_likelihoods_first_T0_steps(self, c: int, T0: int, *, states=None, observations=None):
@@ -294,7 +302,7 @@ class MMLinGaussSS_marginalizable:
         if observations is None:
             tr = self._train_data()
             od = DeviceData.__new__(DeviceData)
-            od.z, od.x, od.T, od.n, od.l, od.d = None, tr.x, tr.T, tr.n, tr.l, None
+            od.z, od.x, od.T, od.n, od.l, od.d, od.perm = None, tr.x, tr.T, tr.n, tr.l, None, tr.perm
             return od
         return DeviceData(None, observations, self.engine.device)
 
@@ -427,7 +435,7 @@ class MMLinGaussSS_marginalizable:
         res = eng.estep(self._train_data(), self._packed_params(), self.n_clusters, self.n_timesteps, assign=assign,
                         count_switches=True)
         _raise_for_status(res["status"], self.alpha)
-        self.cluster_assignment = assign.cpu().numpy().astype(np.int64)
+        self.cluster_assignment = self._assign_host(assign)
         return int(res["n_switches"])
 
     def M_step(self) -> None:
@@ -443,7 +451,7 @@ class MMLinGaussSS_marginalizable:
         assign = self._assign_dev()
         params, info = eng.em_fit(self._train_data(), assign, self.n_clusters, self.alpha, n_steps)
         self.fit_info = info
-        self.cluster_assignment = assign.cpu().numpy().astype(np.int64)
+        self.cluster_assignment = self._assign_host(assign)
         if info["exit"] == "guard0":
             if verbose:
                 print("Encountered near-empty cluster.")
@@ -527,8 +535,9 @@ class MMLinGaussSS_marginalizable:
             a0 = np.stack([np.random.default_rng(seed=100 + i).integers(low=0, high=k, size=n)
                            for i in range(n_starts)]).astype(np.int32)
             assign = torch.from_numpy(a0).to(eng.device)
+        assign = shared.to_resident(assign)
         params, infos, scores, sstat = eng.sweep_fit(shared, assign, k, self.alpha, n_steps)
-        params_h, assign_h = params.cpu().numpy(), assign.cpu().numpy()
+        params_h, assign_h = params.cpu().numpy(), shared.from_resident(assign).cpu().numpy()
         out = []
         for i in range(n_starts):
             info = infos[i]

@@ -290,25 +290,28 @@ def test_scale_properties(mix, eng):
     mdl.train(n_steps=3)
     assert mdl.fit_info["n_e_steps"] == 3
     P = mdl._packed_params()
-    data = mdl._train_data()
+    data = mdl._train_data()  # resident (pattern) order; from_resident gives the caller's order back
+    assert data.perm is not None
     res = eng.estep(data, P, n_c, T, want_ll=True)
-    ll = res["ll"].cpu().numpy()
-    a = res["assign"].cpu().numpy()
+    ll = data.from_resident(res["ll"]).cpu().numpy()
+    a = data.from_resident(res["assign"]).cpu().numpy()
     # (a) oracle on a strided sample of the full-size run
     idx = np.arange(0, n, 97)[:8000]
     llo = oc.seq_loglik_matrix(P, z[:, idx], x[:, idx])
     assert relerr(ll[:, idx], llo) < RTOL
     assert np.array_equal(a[idx], oc.assign(llo, P[:, 0]))
-    # (b) permutation equivariance: shuffling trajectories shuffles the outputs
+    # (b) permutation equivariance: shuffling trajectories shuffles the outputs — bit for bit, although the
+    # pattern-ordered resident set takes the warp-uniform point-mass shortcuts and the shuffled one does not
     perm = rng.permutation(n)
     dp = mtm_b200.DeviceData(z[:, perm], x[:, perm], eng.device)
     rp = eng.estep(dp, P, n_c, T, want_ll=True)
     assert np.array_equal(rp["ll"].cpu().numpy(), ll[:, perm])
     assert np.array_equal(rp["assign"].cpu().numpy(), a[perm])
     # (c) switch count = number of changed labels; cluster sizes consistent
-    old = torch.from_numpy(rng.integers(0, n_c, n).astype(np.int32)).to(eng.device)
-    old_h = old.cpu().numpy().copy()
+    old_h = rng.integers(0, n_c, n).astype(np.int32)
+    old = data.to_resident(old_h)
     r2 = eng.estep(data, P, n_c, T, assign=old, count_switches=True)
+    assert np.array_equal(data.from_resident(old).cpu().numpy(), a)
     assert r2["n_switches"] == int(np.sum(old_h != a))
     assert r2["min_count"] == int(np.bincount(a, minlength=n_c).min())
     # (d) hidden states all NaN through the joint kernel == observation-only kernel
@@ -319,7 +322,8 @@ def test_scale_properties(mix, eng):
     assert relerr(l1, l2) < 1e-13
     # (e) statistics are additive over shards (what the multi-GPU all-reduce relies on)
     at = torch.from_numpy(a.astype(np.int32)).to(eng.device)
-    full = eng.mstats(data, at, n_c).cpu().numpy()
+    at_res = data.to_resident(a.astype(np.int32))
+    full = eng.mstats(data, at_res, n_c).cpu().numpy()
     h = n // 2 + 13
     d1 = mtm_b200.DeviceData(z[:, :h], x[:, :h], eng.device)
     d2 = mtm_b200.DeviceData(z[:, h:], x[:, h:], eng.device)
@@ -330,7 +334,7 @@ def test_scale_properties(mix, eng):
     assert np.array_equal(full[:, 0], np.bincount(a, minlength=n_c).astype(float))
     # (f) M-step from the statistics == numpy M-step of the oracle on a sample-sized problem
     pf, _ = eng.finalize(torch.from_numpy(full).to(eng.device), n_c, d, l, n, 0.0)
-    p2, _, st = eng.mstep(data, at, n_c, 0.0)
+    p2, _, st = eng.mstep(data, at_res, n_c, 0.0)
     assert st == 0 and np.array_equal(pf.cpu().numpy(), p2.cpu().numpy())
 
 
@@ -506,3 +510,56 @@ def test_many_clusters_vs_oracle(mix, n_c):
     assert mdl.fit_info["switches"] == ref.switches
     assert np.array_equal(mdl.cluster_assignment, ref.assign)
     assert relerr(mdl._packed_params(), ref.params.packed()) < RTOL
+
+
+def test_pattern_order(eng):
+    """mtm_pattern_order / mtm_permute_*: a stable sort by the per-step "z complete" pattern; gathers exact;
+    inverse round trip; the E-step gives the same bits in either order (point-mass shortcut vs generic path)."""
+    import mtm_b200
+
+    for (n, T, d, l) in ((70_003, 8, 4, 4), (5_000, 3, 2, 4), (33, 12, 1, 1), (2, 8, 4, 4)):
+        z, x = _synthetic(n, T, d, l, 3, seed=11 + n % 7)
+        z[:, ::5] = np.where(np.isnan(z[:, ::5]), 0.25, z[:, ::5])  # plenty of complete steps
+        z[0, 3 % n, 0] = np.inf
+        ordered = mtm_b200.DeviceData(z, x, eng.device, pattern_order=True)
+        perm = ordered.perm.cpu().numpy()
+        assert np.array_equal(np.sort(perm), np.arange(n))
+        key = np.zeros(n, dtype=np.int64)
+        for t in range(min(T, 8)):
+            key |= np.all(np.isfinite(z[t]), axis=1).astype(np.int64) << t
+        assert np.array_equal(perm, np.argsort(key, kind="stable"))
+        assert np.array_equal(ordered.z.cpu().numpy(), z[:, perm], equal_nan=True)
+        assert np.array_equal(ordered.x.cpu().numpy(), x[:, perm], equal_nan=True)
+        lab = np.random.default_rng(1).integers(0, 3, (2, n)).astype(np.int32)
+        lr = ordered.to_resident(lab)
+        assert np.array_equal(lr.cpu().numpy(), lab[:, perm])
+        assert np.array_equal(ordered.from_resident(lr).cpu().numpy(), lab)
+        if n < 100:
+            continue
+        plain = mtm_b200.DeviceData(z, x, eng.device)
+        mdl_P = eng.mstep(plain, torch.from_numpy(lab[0]).to(eng.device), 3, 0.0)[0]
+        r0 = eng.estep(plain, mdl_P, 3, T, want_ll=True, want_probs=True)
+        r1 = eng.estep(ordered, mdl_P, 3, T, want_ll=True, want_probs=True)
+        assert np.array_equal(ordered.from_resident(r1["ll"]).cpu().numpy(), r0["ll"].cpu().numpy(), equal_nan=True)
+        assert np.array_equal(ordered.from_resident(r1["probs"]).cpu().numpy(), r0["probs"].cpu().numpy(),
+                              equal_nan=True)
+        assert np.array_equal(ordered.from_resident(r1["assign"]).cpu().numpy(), r0["assign"].cpu().numpy())
+
+
+def test_pattern_order_fit_equals_plain_fit(eng):
+    """A whole fit on the pattern-ordered set: same labels and switch history as in the caller's order (the
+    statistics are summed in another order, so parameters agree to rounding, not bit for bit)."""
+    import mtm_b200
+
+    n, T, d, l, n_c = 200_000, 8, 4, 4, 4
+    z, x = _synthetic(n, T, d, l, n_c, seed=21)
+    a0 = np.random.default_rng(42).integers(0, n_c, n).astype(np.int32)
+    plain = mtm_b200.DeviceData(z, x, eng.device)
+    ordered = mtm_b200.DeviceData(z, x, eng.device, pattern_order=True)
+    ap = torch.from_numpy(a0).to(eng.device)
+    ao = ordered.to_resident(a0)
+    pp, ip = eng.em_fit(plain, ap, n_c, 0.0, 6)
+    po, io = eng.em_fit(ordered, ao, n_c, 0.0, 6)
+    assert ip["switches"] == io["switches"] and ip["exit"] == io["exit"]
+    assert np.array_equal(ordered.from_resident(ao).cpu().numpy(), ap.cpu().numpy())
+    assert relerr(po.cpu().numpy(), pp.cpu().numpy()) < 1e-11

@@ -28,16 +28,18 @@ def main():
     if len(sys.argv) > 4:
         lo, hi = int(sys.argv[3], 16), int(sys.argv[4], 16)
     else:
-        best = (0, 0, 0)
+        # the time loop = the shortest loop that holds at least 60 % of the FP64 instructions of the loop
+        # holding the most (outer tile / cluster loops contain it and are longer)
+        fp = ("DFMA", "DMUL", "DADD")
+        loops = []
         for a, op, args in ins:
             if op == "BRA":
                 m = re.search(r"0x([0-9a-f]+)", args)
                 if m and int(m.group(1), 16) < a:
                     t = int(m.group(1), 16)
-                    # innermost big loop: choose the longest loop that contains no other back-edge target... keep simple: longest < 1000 instr
-                    if best[0] < a - t <= 16 * 1000:
-                        best = (a - t, t, a)
-        _, lo, hi = best
+                    loops.append((t, a, sum(1 for x in ins if t <= x[0] <= a and x[1] in fp)))
+        top = max(l[2] for l in loops)
+        lo, hi, _ = min((l for l in loops if l[2] >= 0.6 * top), key=lambda l: l[1] - l[0])
     region = [i for i in ins if lo <= i[0] <= hi]
     cache = {}  # slot -> register kept by the previous instruction
     hist = collections.Counter()
