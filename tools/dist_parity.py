@@ -33,10 +33,11 @@ def main():
         n, T, d, l, n_c, seed, n_steps = (int(v) for v in g[f"{key}_meta"])
         z, x, alpha = g[f"{key}_z"], g[f"{key}_x"], float(g[f"{key}_alpha"])
         lo, hi = mdist.shard_bounds(n, world, rank)
-        data = mtm_b200.DeviceData(z[:, lo:hi], x[:, lo:hi], device)
-        assign = torch.from_numpy(g[f"{key}_assign0"][lo:hi].astype(np.int32)).to(device)
+        # every rank keeps its shard in pattern order (the product path); labels go back to the caller's order
+        data = mtm_b200.DeviceData(z[:, lo:hi], x[:, lo:hi], device, pattern_order=True)
+        assign = data.to_resident(g[f"{key}_assign0"][lo:hi].astype(np.int32))
         params, info = eng.em_fit(data, assign, n_c, alpha, n_steps)
-        full = mdist.gather_assignments(assign, n, world, rank)
+        full = mdist.gather_assignments(data.from_resident(assign), n, world, rank)
         P = params.cpu().numpy()
         err = float(np.max(np.abs(P - g[f"{key}_params"]) / np.maximum(1.0, np.abs(g[f"{key}_params"]))))
         good = (info["switches"] == list(g[f"{key}_switches"]) and np.array_equal(full, g[f"{key}_assign"])
@@ -59,9 +60,9 @@ def main():
     z, x = gr["B_z"], gr["B_x"]
     n, T, d, l, n_c, n_starts = (int(v) for v in gr["B_meta"])
     lo, hi = mdist.shard_bounds(n, world, rank)
-    data = mtm_b200.DeviceData(z[:, lo:hi], x[:, lo:hi], device)
+    data = mtm_b200.DeviceData(z[:, lo:hi], x[:, lo:hi], device, pattern_order=True)
     a0 = np.stack([np.random.default_rng(100 + i).integers(0, n_c, n)[lo:hi] for i in range(n_starts)]).astype(np.int32)
-    assign = torch.from_numpy(a0).to(device)
+    assign = data.to_resident(a0)
     P, infos, scores, sstat = eng.sweep_fit(data, assign, n_c, 0.0, 100)
     ref_obj = gr["B_objectives"][1:]  # [0] is the k-means start
     err = float(np.max(np.abs(scores[:, 0] - ref_obj) / np.abs(ref_obj)))
