@@ -288,6 +288,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT; stdout carries one JSON line
         dist.init_process_group("nccl", device_id=device)
     eng = mtm_b200.Engine.get(device)
     if world > 1:

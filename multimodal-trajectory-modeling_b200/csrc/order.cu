@@ -10,8 +10,8 @@
 // stay reproducible run to run.
 //
 // Key of trajectory i: bit t (t < min(T, 8)) is set iff all d coordinates of z[t, i, :] are finite.
-// Sort: (1) every warp histograms its contiguous chunk of trajectories; (2) one block turns the
-// (bucket-major, warp-minor) table into start offsets; (3) every warp walks its chunk again and hands out
+// Sort: (1) every warp histograms its contiguous chunk of trajectories; (2) the (bucket-major, warp-minor)
+// table is turned into start offsets (one block per bucket); (3) every warp walks its chunk again and hands out
 // positions in trajectory order.  perm[p] = original index of the trajectory at resident position p.
 #include "common.cuh"
 
@@ -57,37 +57,55 @@ __global__ void __launch_bounds__(kOThreads) order_hist_kernel(const double *__r
     for (int b = lane; b < kBuckets; b += 32) hist[(size_t)b * units + unit] = s_cnt[warp][b];
 }
 
-// in-place exclusive prefix sum over `count` entries, one block
-__global__ void __launch_bounds__(1024) order_scan_kernel(unsigned int *v, int64_t count) {
-    __shared__ unsigned long long s_sum[1024];
+// Start offsets from the (bucket-major, warp-minor) histogram, in two levels: block b turns row b into its
+// exclusive prefix sums (coalesced, block-wide scan per 1024-entry chunk) and records the row total; the scatter
+// kernel adds the exclusive sum of the totals of the earlier rows.
+__global__ void __launch_bounds__(1024) order_scan_rows_kernel(unsigned int *hist, int units, unsigned int *row_total) {
+    __shared__ unsigned int s[1024];
+    __shared__ unsigned int s_carry;
+    unsigned int *row = hist + (size_t)blockIdx.x * units;
     const int tid = threadIdx.x;
-    const int64_t seg = (count + 1023) / 1024;
-    const int64_t lo = (int64_t)tid * seg, hi = lo + seg < count ? lo + seg : count;
-    unsigned long long s = 0;
-    for (int64_t k = lo; k < hi; ++k) s += v[k];
-    s_sum[tid] = s;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the segment sums
-        const unsigned long long add = tid >= o ? s_sum[tid - o] : 0;
+    for (int base = 0; base < units; base += 1024) {
+        const int k = base + tid;
+        const unsigned int v = k < units ? row[k] : 0u;
+        s[tid] = v;
         __syncthreads();
-        s_sum[tid] += add;
+        for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+            const unsigned int add = tid >= o ? s[tid - o] : 0u;
+            __syncthreads();
+            s[tid] += add;
+            __syncthreads();
+        }
+        const unsigned int carry = s_carry;
+        if (k < units) row[k] = carry + s[tid] - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s[1023];
         __syncthreads();
     }
-    unsigned long long run = tid ? s_sum[tid - 1] : 0;
-    for (int64_t k = lo; k < hi; ++k) {
-        const unsigned int c = v[k];
-        v[k] = (unsigned int)run;
-        run += c;
-    }
+    if (tid == 0) row_total[blockIdx.x] = s_carry;
 }
 
 __global__ void __launch_bounds__(kOThreads) order_scatter_kernel(const unsigned char *__restrict__ keys, int64_t n,
                                                                    int64_t per, const unsigned int *__restrict__ offs,
-                                                                   int units, int64_t *perm) {
+                                                                   const unsigned int *__restrict__ row_total, int units,
+                                                                   int64_t *perm) {
     __shared__ unsigned int s_pos[kOWarps][kBuckets];
+    __shared__ unsigned int s_base[kBuckets];
+    static_assert(kOThreads == kBuckets, "one thread per bucket for the base scan");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int unit = blockIdx.x * kOWarps + warp;
-    for (int b = lane; b < kBuckets; b += 32) s_pos[warp][b] = offs[(size_t)b * units + unit];
+    s_base[threadIdx.x] = row_total[threadIdx.x];
+    __syncthreads();
+    for (int o = 1; o < kBuckets; o <<= 1) {  // inclusive scan of the bucket sizes
+        const unsigned int add = threadIdx.x >= o ? s_base[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_base[threadIdx.x] += add;
+        __syncthreads();
+    }
+    for (int b = lane; b < kBuckets; b += 32)
+        s_pos[warp][b] = offs[(size_t)b * units + unit] + (b ? s_base[b - 1] : 0u);
     __syncwarp();
     const int64_t lo = (int64_t)unit * per;
     const int64_t hi = lo + per < n ? lo + per : n;
@@ -130,7 +148,7 @@ __global__ void __launch_bounds__(256) permute_rows_kernel(const T *__restrict__
 int order_units(int sm_count) { return sm_count * 4 * kOWarps; }  // warps of the sort grid
 
 size_t order_scratch_bytes(int64_t n, int sm_count) {
-    return (size_t)kBuckets * order_units(sm_count) * sizeof(unsigned int) + (size_t)n + 256;
+    return (size_t)kBuckets * (order_units(sm_count) + 1) * sizeof(unsigned int) + (size_t)n + 256;
 }
 
 cudaError_t launch_pattern_order(const double *z, int64_t n, int64_t ld, int T, int d, int sm_count, void *scratch,
@@ -138,13 +156,14 @@ cudaError_t launch_pattern_order(const double *z, int64_t n, int64_t ld, int T, 
     const int units = order_units(sm_count);
     const int grid = units / kOWarps;
     unsigned int *hist = static_cast<unsigned int *>(scratch);
-    unsigned char *keys = reinterpret_cast<unsigned char *>(hist + (size_t)kBuckets * units);
+    unsigned int *row_total = hist + (size_t)kBuckets * units;
+    unsigned char *keys = reinterpret_cast<unsigned char *>(row_total + kBuckets);
     int64_t per = (n + units - 1) / units;
     per = (per + 31) / 32 * 32;
     const int Tk = T < 8 ? T : 8;
     order_hist_kernel<<<grid, kOThreads, 0, s>>>(z, n, ld, Tk, d, per, keys, hist, units);
-    order_scan_kernel<<<1, 1024, 0, s>>>(hist, (int64_t)kBuckets * units);
-    order_scatter_kernel<<<grid, kOThreads, 0, s>>>(keys, n, per, hist, units, perm);
+    order_scan_rows_kernel<<<kBuckets, 1024, 0, s>>>(hist, units, row_total);
+    order_scatter_kernel<<<grid, kOThreads, 0, s>>>(keys, n, per, hist, row_total, units, perm);
     return cudaGetLastError();
 }
 
