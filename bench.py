@@ -287,9 +287,12 @@ def main():
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner at
+    # communicator creation) goes to stderr; fd 1 is restored right before the line is printed
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT; stdout carries one JSON line
         dist.init_process_group("nccl", device_id=device)
     eng = mtm_b200.Engine.get(device)
     if world > 1:
@@ -493,10 +496,13 @@ def main():
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_base, "parity": parity,
                 "present_scalars_per_trajectory": {"z": kz, "x": kx}}
-        print(json.dumps(line))
     if world > 1:
         eng.comm_destroy()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
