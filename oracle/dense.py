@@ -274,6 +274,65 @@ def bic(par, states, observations, ll=None):
 
 
 # --------------------------------------------------------------------------
+# secondary predictors built on the E-step                   MMM:532-577, 808-995, 1077-1123
+# --------------------------------------------------------------------------
+
+
+def propensities_over_time(par: Params, states, observations):
+    """(T, n, n_c): membership probabilities from the first t+1 steps (MMM:532-577)."""
+    T = states.shape[0]
+    with np.errstate(all="ignore"):
+        pc = np.stack([(par.pi[:, None] * np.exp(loglik_matrix(par, states, observations, t + 1))).T for t in range(T)])
+        return pc / np.sum(pc, axis=-1, keepdims=True)
+
+
+def obs_propensities_over_time(par: Params, observations):
+    """(T, n, n_c): the same from the measurements alone (MMM:1077-1123)."""
+    with np.errstate(all="ignore"):
+        pc = np.stack([(par.pi[:, None] * np.exp(obs_loglik_matrix(par, observations, t + 1))).T
+                       for t in range(observations.shape[0])])
+        return pc / np.sum(pc, axis=-1, keepdims=True)
+
+
+def initial_assignment(par: Params, states, observations):
+    """argmax from the first time step only (MMM:909-941)."""
+    return assign_from_loglik(par.pi, loglik_matrix(par, states, observations, 1))
+
+
+def predictions_from_initial(par: Params, states, observations):
+    """Noise-free roll-out z_1 A^t, z_1 A^t H under the cluster chosen from the first step (MMM:943-995)."""
+    a = initial_assignment(par, states, observations)
+    ps, po = np.zeros_like(states), np.zeros_like(observations)
+    for i in range(states.shape[1]):
+        zt = states[0, i, :]
+        for t in range(max(ps.shape[0], po.shape[0])):
+            if t < ps.shape[0]:
+                ps[t, i, :] = zt
+            if t < po.shape[0]:
+                po[t, i, :] = zt @ par.H[a[i]]
+            zt = zt @ par.A[a[i]]
+    return ps, po
+
+
+def one_step_ahead(par: Params, states, observations, history=True):
+    """Probability-weighted one-step-ahead means from the last row (MMM:808-907); history=False keeps only
+    the last step when computing the membership probabilities."""
+    if history:
+        s0, o0 = states, observations
+    else:
+        s0, o0 = np.nan * np.ones_like(states), np.nan * np.ones_like(observations)
+        s0[-1], o0[-1] = states[-1], observations[-1]
+    probs = assign_from_loglik(par.pi, loglik_matrix(par, s0, o0), want_probs=True)[1]
+    nxt_s = np.zeros((1, *states.shape[1:]))
+    nxt_o = np.zeros((1, *observations.shape[1:]))
+    for c in range(par.n_clusters):
+        s_c = states[-1] @ par.A[c]
+        nxt_s += probs[c][:, None] * s_c
+        nxt_o += probs[c][:, None] * (s_c @ par.H[c])
+    return nxt_s, nxt_o
+
+
+# --------------------------------------------------------------------------
 # M-step                                                     MMM:1167-1308
 # --------------------------------------------------------------------------
 

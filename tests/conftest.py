@@ -36,5 +36,10 @@ def g_restarts():
 
 
 @pytest.fixture(scope="session")
+def g_pred():
+    return load_golden("predictors.npz")
+
+
+@pytest.fixture(scope="session")
 def g_adni():
     return load_golden("adni_fold0.npz")

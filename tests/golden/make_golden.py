@@ -392,9 +392,54 @@ def golden_lg_component(ssm):
     print("lg_component.npz written")
 
 
+# ---------------------------------------------------------------------------
+# 6. secondary predictors built on the E-step
+# ---------------------------------------------------------------------------
+
+
+def golden_predictors(ssm, mmm):
+    """cluster_propensities_over_time (MMM:532-577), observed_cluster_propensities_over_time (:1077-1123),
+    initial_full_data_cluster_assignment (:909-941), predictions_from_initial_data (:943-995),
+    one_step_ahead_predictions[_no_history] (:808-907), the T0-prefix likelihoods (:439-494, 997-1048) and
+    aic / bic (:668-722) of one trained model, on its training set and on held-out trajectories."""
+    out = {}
+    rng = np.random.default_rng(77)
+    n_tr, n_te, T, d, l, n_c = 400, 150, 5, 2, 3, 3
+    z, x, lab, comps = sample_mixture(ssm, rng, n_tr + n_te, T, d, l, n_c, 0.2)
+    z[0] = np.where(np.isnan(z[0]), 0.1, z[0])  # predictions_from_initial_data asserts on a complete first state
+    ztr, xtr, zte, xte = z[:, :n_tr].copy(), x[:, :n_tr].copy(), z[:, n_tr:].copy(), x[:, n_tr:].copy()
+    mdl = mmm.MMLinGaussSS_marginalizable(n_clusters=n_c, states=ztr, observations=xtr, random_seed=5)
+    mdl.train(n_steps=40)
+    assert min(np.bincount(mdl.cluster_assignment, minlength=n_c)) >= 20
+    out.update(ztr=ztr, xtr=xtr, zte=zte, xte=xte, params=pack_model(mdl), assign=np.array(mdl.cluster_assignment),
+               seed=5)
+    out["pot_tr"] = mdl.cluster_propensities_over_time(states=ztr, observations=xtr)
+    out["pot_te"] = mdl.cluster_propensities_over_time(states=zte, observations=xte)
+    out["opot_tr"] = mdl.observed_cluster_propensities_over_time()
+    out["opot_te"] = mdl.observed_cluster_propensities_over_time(observations=xte)
+    out["init_tr"] = mdl.initial_full_data_cluster_assignment()
+    out["init_te"] = mdl.initial_full_data_cluster_assignment(states=zte, observations=xte)
+    ps, po = mdl.predictions_from_initial_data()
+    out.update(pfi_s=ps, pfi_o=po)
+    s1, o1 = mdl.one_step_ahead_predictions(states=zte, observations=xte)
+    s2, o2 = mdl.one_step_ahead_predictions_no_history(states=zte, observations=xte)
+    out.update(osa_s=s1, osa_o=o1, osanh_s=s2, osanh_o=o2)
+    for T0 in (1, 3, T):
+        out[f"ll_T{T0}"] = np.stack([mdl.conditional_log_likelihoods_first_T0_steps(c, T0) for c in range(n_c)])
+        out[f"oll_T{T0}_te"] = np.stack([mdl.observed_condl_log_lik_first_T0_steps(c, T0, observations=xte)
+                                         for c in range(n_c)])
+    out.update(aic=mdl.aic(), bic=mdl.bic(), aic_te=mdl.aic(states=zte, observations=xte),
+               bic_te=mdl.bic(states=zte, observations=xte), n_free=mdl.n_free_params,
+               Q=mdl.e_complete_data_log_lik(), LL=mdl.model_log_likelihood())
+    np.savez_compressed(os.path.join(HERE, "predictors.npz"), **out)
+    print("predictors.npz written")
+
+
 if __name__ == "__main__":
     ssm, mmm, uss = import_reference()
-    which = sys.argv[1:] or ["ssm", "em", "restarts", "adni", "lg"]
+    which = sys.argv[1:] or ["ssm", "em", "restarts", "adni", "lg", "pred"]
+    if "pred" in which:
+        golden_predictors(ssm, mmm)
     if "ssm" in which:
         golden_ssm(ssm)
     if "em" in which:

@@ -563,3 +563,39 @@ def test_pattern_order_fit_equals_plain_fit(eng):
     assert ip["switches"] == io["switches"] and ip["exit"] == io["exit"]
     assert np.array_equal(ordered.from_resident(ao).cpu().numpy(), ap.cpu().numpy())
     assert relerr(po.cpu().numpy(), pp.cpu().numpy()) < 1e-11
+
+
+def test_secondary_predictors(g_pred, mix):
+    """SURVEY 8 f3 through the drop-in class: a model trained here from the reference's seed must reproduce
+    the reference's fit, and every predictor layered on the E-step must match the reference's outputs."""
+    g = g_pred
+    ztr, xtr, zte, xte = g["ztr"], g["xtr"], g["zte"], g["xte"]
+    n_c, T = g["params"].shape[0], ztr.shape[0]
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=n_c, states=ztr, observations=xtr, random_seed=int(g["seed"]))
+    mdl.train(n_steps=40)
+    assert np.array_equal(mdl.cluster_assignment, g["assign"])
+    assert relerr(mdl._packed_params(), g["params"]) < RTOL
+    assert relerr(mdl.cluster_propensities_over_time(states=ztr, observations=xtr), g["pot_tr"]) < RTOL
+    assert relerr(mdl.cluster_propensities_over_time(), g["pot_tr"]) < RTOL  # resident (pattern-ordered) set
+    assert relerr(mdl.cluster_propensities_over_time(states=zte, observations=xte), g["pot_te"]) < RTOL
+    assert relerr(mdl.observed_cluster_propensities_over_time(), g["opot_tr"]) < RTOL
+    assert relerr(mdl.observed_cluster_propensities_over_time(observations=xte), g["opot_te"]) < RTOL
+    assert np.array_equal(mdl.initial_full_data_cluster_assignment(), g["init_tr"])
+    assert np.array_equal(mdl.initial_full_data_cluster_assignment(states=zte, observations=xte), g["init_te"])
+    ps, po = mdl.predictions_from_initial_data()
+    assert relerr(ps, g["pfi_s"]) < RTOL and relerr(po, g["pfi_o"]) < RTOL
+    s1, o1 = mdl.one_step_ahead_predictions(states=zte, observations=xte)
+    assert relerr(s1, g["osa_s"]) < RTOL and relerr(o1, g["osa_o"]) < RTOL
+    s2, o2 = mdl.one_step_ahead_predictions_no_history(states=zte, observations=xte)
+    assert relerr(s2, g["osanh_s"]) < RTOL and relerr(o2, g["osanh_o"]) < RTOL
+    for T0 in (1, 3, T):
+        ll = np.stack([mdl.conditional_log_likelihoods_first_T0_steps(c, T0) for c in range(n_c)])
+        assert relerr(ll, g[f"ll_T{T0}"]) < RTOL
+        assert relerr(mdl.log_likelihood_matrix(T0=T0), g[f"ll_T{T0}"]) < RTOL
+        oll = np.stack([mdl.observed_condl_log_lik_first_T0_steps(c, T0, observations=xte) for c in range(n_c)])
+        assert relerr(oll, g[f"oll_T{T0}_te"]) < RTOL
+    for name, val in (("aic", mdl.aic()), ("bic", mdl.bic()), ("aic_te", mdl.aic(states=zte, observations=xte)),
+                      ("bic_te", mdl.bic(states=zte, observations=xte)), ("Q", mdl.e_complete_data_log_lik()),
+                      ("LL", mdl.model_log_likelihood())):
+        assert abs(val - float(g[name])) < RTOL * abs(float(g[name])), name
+    assert mdl.n_free_params == int(g["n_free"])
