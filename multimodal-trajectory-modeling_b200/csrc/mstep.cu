@@ -16,6 +16,8 @@
 // atomics anywhere, the summation order is a pure function of (n, grid).  Block sums are carried
 // as double-double (hi, lo) pairs across tiles and blocks, so the accumulated rounding error does
 // not grow with n.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "filter.cuh"
 #include "stats_tile.cuh"
@@ -429,7 +431,14 @@ size_t stats_smem(int n_c, int d, int l) { return stats_smem_bytes(n_c, d, l); }
 
 int stats_grid(int64_t n, int sm_count) {
     const int64_t tiles = (n + kSThreads - 1) / kSThreads;
-    const int64_t cap = (int64_t)sm_count * 4;
+    // 3 blocks are resident per SM (166 registers, 62 KB of shared memory): the grid must be a multiple of that,
+    // 4 per SM ran 1.33 waves (4.47 ms at 10 M trajectories; 3 / 6 / 12 / 24 per SM: 3.21 / 3.16 / 3.25 / 3.19 ms)
+    int per_sm = 6;
+    if (const char *e = getenv("MTM_STATS_BLOCKS_PER_SM")) {  // tuning knob
+        const int v = atoi(e);
+        if (v > 0) per_sm = v;
+    }
+    const int64_t cap = (int64_t)sm_count * per_sm;
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
