@@ -127,6 +127,16 @@ int mtm_estep(mtm_handle *h, const mtm_data *data, const double *params_dev, int
               int32_t *assign_dev, int count_switches, double *ll_dev, double *probs_dev,
               double *prenorm_dev, mtm_estep_info *info);
 
+/* ---- all prefix log-likelihoods in one pass ------------------------------------------------------
+ * ll_prefix_dev (T0, n_c, n) float64 out: ll_prefix[t, c, i] = conditional_log_likelihoods_first_T0_steps(c, t + 1)[i]
+ * (MMM:439-494; with data->z_dev == NULL observed_condl_log_lik_first_T0_steps, MMM:997-1048) for every
+ * t < T0 at once.  This is what cluster_propensities_over_time / observed_cluster_propensities_over_time
+ * (MMM:532-577, 1077-1123) need; the reference filters T0 (T0 + 1) / 2 steps per (trajectory, cluster) for
+ * it, the sequential filter passes through every prefix anyway.
+ * status_host (nullable): MTM_STATUS_* bits; when given the call synchronises. */
+int mtm_estep_prefix(mtm_handle *h, const mtm_data *data, const double *params_dev, int n_c, int T0,
+                     double *ll_prefix_dev, int32_t *status_host);
+
 /* ---- scores -----------------------------------------------------------------------------------
  * out_host[0] = Q  = sum_i log pi_{a_i} + ll[a_i, i] with a = argmax   (e_complete_data_log_lik, MMM:579-624)
  * out_host[1] = LL = sum_i log sum_c pi_c exp(ll[c,i])                  (model_log_likelihood,   MMM:626-666)

@@ -59,6 +59,7 @@ SIGNATURES = {
     "mtm_stats_stride": (_i, [_i, _i]),
     "mtm_set_data": (_i, [_vp, ctypes.POINTER(MtmData)]),
     "mtm_estep": (_i, [_vp, ctypes.POINTER(MtmData), _vp, _i, _i, _vp, _i, _vp, _vp, _vp, ctypes.POINTER(EStepInfo)]),
+    "mtm_estep_prefix": (_i, [_vp, ctypes.POINTER(MtmData), _vp, _i, _i, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "mtm_score": (_i, [_vp, ctypes.POINTER(MtmData), _vp, _i, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int32)]),
     "mtm_mstats": (_i, [_vp, _vp, _i, _vp]),
     "mtm_finalize": (_i, [_vp, _vp, _i, _i, _i, _i64, _d, _vp, _vp]),

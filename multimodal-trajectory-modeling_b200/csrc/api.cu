@@ -461,6 +461,37 @@ int mtm_estep(mtm_handle *h, const mtm_data *data, const double *params_dev, int
     return 0;
 }
 
+int mtm_estep_prefix(mtm_handle *h, const mtm_data *data, const double *params_dev, int n_c, int T0,
+                     double *ll_prefix_dev, int32_t *status_host) {
+    if (!h || !ll_prefix_dev) return -1;
+    const mtm_data *dt = data ? data : (h->has_data ? &h->data : nullptr);
+    if (int rc = check_dims(h, dt, n_c)) return rc;
+    if (!params_dev) return fail(h, -1, "params_dev is NULL");
+    DeviceGuard g(h->device);
+    EStepArgs a{};
+    a.z = dt->z_dev;
+    a.x = dt->x_dev;
+    a.n = dt->n;
+    a.ld = dt->ld > 0 ? dt->ld : dt->n;
+    a.T = dt->T;
+    a.T0 = T0 < 1 ? 1 : (T0 > dt->T ? dt->T : T0);
+    a.d = dt->d;
+    a.l = dt->l;
+    a.params = params_dev;
+    a.n_c = n_c;
+    a.ctrl = h->d_ctrl;
+    const size_t smem = (size_t)n_c * param_stride(a.d, a.l) * 8 + (size_t)n_c * a.T0 * 4 + 16;
+    if (smem > 200 * 1024) return fail(h, -1, "shared memory %zu B too large (n_c * T0 too big)", smem);
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    MTM_CUDA(h, launch_estep_prefix(a, ll_prefix_dev, estep_grid(dt->n, h->sm_count, false), h->stream));
+    h->launches += 1;
+    if (status_host) {
+        if (int rc = read_ctrl(h)) return rc;
+        *status_host = h->h_ctrl->status;
+    }
+    return 0;
+}
+
 int mtm_score(mtm_handle *h, const mtm_data *data, const double *params_dev, int n_c, double *out_host,
               int32_t *status_host) {
     if (!h || !out_host) return -1;

@@ -85,6 +85,7 @@ cudaError_t launch_p2p_allreduce(double *buf, int count, const P2PView &v, unsig
 
 // launchers (one translation unit per kernel family so that nvcc can build them in parallel)
 cudaError_t launch_estep(const EStepArgs &a, int grid, size_t smem, cudaStream_t s);
+cudaError_t launch_estep_prefix(const EStepArgs &a, double *pre, int grid, cudaStream_t s);  // pre: (T0, n_c, n)
 int estep_grid(int64_t n, int sm_count, bool fused);
 size_t estep_smem(int n_c, int T0, int d, int l, bool fused);
 

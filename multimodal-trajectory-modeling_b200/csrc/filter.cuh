@@ -478,10 +478,14 @@ __device__ __forceinline__ void load_row(const double *__restrict__ p, double (&
 // warp-uniform branch that is never taken.  With the same code shape as the joint kernel ptxas 12.9 keeps the
 // uniform-datapath parameter operands there too (modelled FP64-pipe efficiency 0.89 instead of 0.80,
 // tools/sass_reuse.py); the null z pointer is never dereferenced.
-template <class DM, bool HAS_Z, class PS>
+// PREFIX = true (estep_prefix.cu only): after every step t the log-likelihood of the first t+1 steps is
+// written to pre[t * pre_stride] — the sequential form has every prefix likelihood for free
+// (cluster_propensities_over_time, MMM:532-577, needs all of them).
+template <class DM, bool HAS_Z, class PS, bool PREFIX = false>
 __device__ __forceinline__ double filter_eval(const DM &dm, const double *__restrict__ z_i, int64_t zs,
                                               const double *__restrict__ x_i, int64_t xs, int T0,
-                                              const PS &psrc, const uint32_t *fin, int &bad, int tshift) {
+                                              const PS &psrc, const uint32_t *fin, int &bad, int tshift,
+                                              double *pre = nullptr, int64_t pre_stride = 0) {
     FilterState<DM> f;
     {
         const ParamView<DM, PS> p0(dm, psrc);
@@ -528,6 +532,7 @@ __device__ __forceinline__ double filter_eval(const DM &dm, const double *__rest
         else filter_condition_x(dm, f, p, xt, fm >> 16, last);
         p_point = z_point;
         filter_rescale(f);
+        if (PREFIX) pre[(int64_t)t * pre_stride] = filter_finish(f, bad);
 #define MTM_PINNED_COPY(dst, src)                                                                   \
     asm volatile("{ .reg .pred pp; setp.ne.s32 pp, %2, 0x7fffffff; @pp mov.f64 %0, %1; }" \
                  : "+d"(dst) : "d"(src), "r"(f.expo))

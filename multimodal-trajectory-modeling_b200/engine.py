@@ -172,6 +172,19 @@ class Engine:
         return dict(assign=assign, ll=ll, probs=probs, prenorm=prenorm, n_switches=int(info.n_switches),
                     min_count=int(info.min_count), status=int(info.status))
 
+    def estep_prefix(self, data: DeviceData, params, n_c, T0, d=None):
+        """(T0, n_c, n) log-likelihoods of every prefix 1..T0 in one launch (mtm_estep_prefix), resident order.
+        Returns (tensor, status)."""
+        self._sync_stream()
+        st = data.struct(d)
+        params = self.dev(params, torch.float64)
+        T0 = max(1, min(int(T0), data.T))
+        out = torch.empty((T0, n_c, data.n), dtype=torch.float64, device=self.device)
+        status = ctypes.c_int32(0)
+        self._chk(self.lib.mtm_estep_prefix(self.h, ctypes.byref(st), ctypes.c_void_p(params.data_ptr()), n_c, T0,
+                                            ctypes.c_void_p(out.data_ptr()), ctypes.byref(status)))
+        return out, int(status.value)
+
     def score(self, data: DeviceData, params, n_c, d=None):
         self._sync_stream()
         st = data.struct(d)

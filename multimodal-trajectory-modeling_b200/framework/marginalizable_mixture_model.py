@@ -283,11 +283,15 @@ class MMLinGaussSS_marginalizable:
     def cluster_propensities_over_time(self, *, states=None, observations=None):
         """(T, n, n_c) membership probabilities from the first t+1 steps (MMM:532-577)."""
         data = self._resolve(states, observations)
-        out = []
-        for t in range(min(self.n_timesteps, data.T)):
-            L = self._estep(data, t + 1, ll=True)["ll"].cpu().numpy()
-            out.append((self.cluster_propensities[:, None] * np.exp(L)).T)
-        pc_t = np.stack(out, axis=0)
+        return self._propensities_over_time(data, min(self.n_timesteps, data.T), None)
+
+    def _propensities_over_time(self, data, T0, d):
+        """All T0 prefixes from ONE launch (mtm_estep_prefix): the sequential filter passes through every
+        prefix likelihood anyway; the reference re-evaluates each prefix from scratch."""
+        L, status = self.engine.estep_prefix(data, self._packed_params(), self.n_clusters, T0, d=d)
+        _raise_for_status(status, self.alpha)
+        L = data.from_resident(L.reshape(T0 * self.n_clusters, data.n)).reshape(T0, self.n_clusters, data.n)
+        pc_t = self.cluster_propensities[None, None, :] * np.exp(L.cpu().numpy().transpose(0, 2, 1))
         pc_t /= np.sum(pc_t, axis=-1, keepdims=True)
         assert np.all(pc_t >= 0.0) and np.allclose(np.sum(pc_t, axis=-1), 1.0)
         return pc_t
@@ -318,14 +322,7 @@ class MMLinGaussSS_marginalizable:
     def observed_cluster_propensities_over_time(self, observations=None):
         """MMM:1077-1123."""
         data = self._obs_data(observations)
-        out = []
-        for t in range(data.T):
-            L = self._estep(data, t + 1, ll=True, d=self.d_states)["ll"].cpu().numpy()
-            out.append((self.cluster_propensities[:, None] * np.exp(L)).T)
-        pc_t = np.stack(out, axis=0)
-        pc_t /= np.sum(pc_t, axis=-1, keepdims=True)
-        assert np.all(pc_t >= 0.0) and np.allclose(np.sum(pc_t, axis=-1), 1.0)
-        return pc_t
+        return self._propensities_over_time(data, data.T, self.d_states)
 
     def observations_mle_cluster_assignment(self, *, return_probs: bool = False, observations=None):
         """argmax over p(x | c) pi_c  [, probs]  (MMM:1125-1165)."""

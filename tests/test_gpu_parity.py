@@ -599,3 +599,23 @@ def test_secondary_predictors(g_pred, mix):
                       ("LL", mdl.model_log_likelihood())):
         assert abs(val - float(g[name])) < RTOL * abs(float(g[name])), name
     assert mdl.n_free_params == int(g["n_free"])
+
+
+@pytest.mark.parametrize("shape", [(3001, 8, 4, 4, 3), (700, 5, 2, 3, 4), (257, 4, 6, 2, 2), (129, 12, 1, 1, 2)])
+def test_prefix_loglik_one_pass(eng, shape):
+    """mtm_estep_prefix: every prefix log-likelihood from one launch equals the per-T0 E-step (same bits), joint
+    and observation-only, static and run-time dimensions, pattern-ordered or not."""
+    import mtm_b200
+
+    n, T, d, l, n_c = shape
+    z, x = _synthetic(n, T, d, l, n_c, seed=31 + n % 5)
+    lab = torch.from_numpy(np.random.default_rng(3).integers(0, n_c, n).astype(np.int32)).to(eng.device)
+    plain = mtm_b200.DeviceData(z, x, eng.device)
+    P = eng.mstep(plain, lab, n_c, 0.0)[0]
+    for data, dd in ((plain, None), (mtm_b200.DeviceData(z, x, eng.device, pattern_order=True), None),
+                     (mtm_b200.DeviceData(None, x, eng.device), d)):
+        pre, status = eng.estep_prefix(data, P, n_c, T, d=dd)
+        assert status == 0 and tuple(pre.shape) == (T, n_c, n)
+        for T0 in range(1, T + 1):
+            ll = eng.estep(data, P, n_c, T0, want_ll=True, d=dd)["ll"]
+            assert torch.equal(pre[T0 - 1], ll), (shape, T0)
