@@ -619,3 +619,45 @@ def test_prefix_loglik_one_pass(eng, shape):
         for T0 in range(1, T + 1):
             ll = eng.estep(data, P, n_c, T0, want_ll=True, d=dd)["ll"]
             assert torch.equal(pre[T0 - 1], ll), (shape, T0)
+
+
+def test_full_size_properties(eng):
+    """BASELINE config 3 at its full size (10 M trajectories, T = 8, d = l = 4, n_c = 8, 20 % missing; generated
+    on the device): oracle-free properties of two EM iterations — same labels and switch counts on the
+    pattern-ordered set and in the caller's order, cluster sizes add up, the statistics of two shards add up to
+    those of the whole, and an oracle check of the log-likelihoods on a strided sample."""
+    import bench
+    import mtm_b200
+    from oracle import cport as oc
+
+    n, T, d, l, n_c = 10_000_000, 8, 4, 4, 8
+    z, x = bench.sample_device(n, T, d, l, bench.mixture_params(n_c, d, l), seed=4321, device=eng.device)
+    gen = torch.Generator(device=eng.device)
+    gen.manual_seed(42)
+    a0 = torch.randint(0, n_c, (n,), generator=gen, device=eng.device, dtype=torch.int32)
+    plain = mtm_b200.DeviceData(z, x, eng.device)
+    ordered = mtm_b200.DeviceData(z, x, eng.device, pattern_order=True)
+    ap, ao = a0.clone(), ordered.to_resident(a0)
+    pp, ip = eng.em_fit(plain, ap, n_c, 0.0, 2)
+    po, io = eng.em_fit(ordered, ao, n_c, 0.0, 2)
+    assert ip["switches"] == io["switches"] and ip["n_e_steps"] == 2
+    back = ordered.from_resident(ao)
+    assert torch.equal(back, ap)
+    assert relerr(po.cpu().numpy(), pp.cpu().numpy()) < 1e-11
+    sizes = torch.bincount(ap.long(), minlength=n_c)
+    assert int(sizes.sum()) == n and io["min_count"] == int(sizes.min())
+    # shard additivity of the statistics (what the all-reduce relies on), at full size
+    full = eng.mstats(plain, ap, n_c)
+    h = n // 2 + 12345
+    s1 = eng.mstats(mtm_b200.DeviceData(z[:, :h].contiguous(), x[:, :h].contiguous(), eng.device), ap[:h].contiguous(), n_c)
+    s2 = eng.mstats(mtm_b200.DeviceData(z[:, h:].contiguous(), x[:, h:].contiguous(), eng.device), ap[h:].contiguous(), n_c)
+    assert relerr((s1 + s2).cpu().numpy(), full.cpu().numpy()) < 1e-12
+    assert torch.equal(full[:, 0], sizes.double())
+    # oracle on a strided sample of the full-size E-step
+    idx = torch.arange(0, n, 4999, device=eng.device)
+    sub = mtm_b200.DeviceData(z[:, idx].contiguous(), x[:, idx].contiguous(), eng.device)
+    r = eng.estep(sub, pp, n_c, T, want_ll=True)
+    P = pp.cpu().numpy()
+    llo = oc.seq_loglik_matrix(P, sub.z.cpu().numpy(), sub.x.cpu().numpy())
+    assert relerr(r["ll"].cpu().numpy(), llo) < RTOL
+    assert np.array_equal(r["assign"].cpu().numpy(), oc.assign(llo, P[:, 0]))
