@@ -41,5 +41,10 @@ def g_pred():
 
 
 @pytest.fixture(scope="session")
+def g_ext():
+    return load_golden("extended.npz")
+
+
+@pytest.fixture(scope="session")
 def g_adni():
     return load_golden("adni_fold0.npz")

@@ -8,7 +8,7 @@ GPU box):
 
 The reference is imported from /root/reference with ``sys.modules`` stubs for the two
 absent plotting/reporting packages (matplotlib, statsmodels — only used by plotting and
-``print_tests``) and ``np.alltrue`` shimmed.  ``use_cache=False`` everywhere because the
+``print_tests``) and ``np.alltrue`` / ``np.infty`` shimmed.  ``use_cache=False`` everywhere because the
 reference directory is read-only.  Output: ``tests/golden/*.npz`` (committed).
 """
 
@@ -31,6 +31,10 @@ def import_reference():
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     if not hasattr(np, "alltrue"):
         np.alltrue = np.all
+    try:
+        np.infty
+    except AttributeError:
+        np.infty = np.inf  # removed in numpy 2; framework_extended/state_space_model_mixture.py still uses it
     sys.path.insert(0, REF)
     from framework import marginalizable_mixture_model as mmm
     from framework import marginalizable_state_space_model as ssm
@@ -435,8 +439,52 @@ def golden_predictors(ssm, mmm):
     print("predictors.npz written")
 
 
+# ---------------------------------------------------------------------------
+# 7. framework_extended mixture and classifier with linear-Gaussian components
+# ---------------------------------------------------------------------------
+
+
+def golden_extended(ssm):
+    from framework_extended import state_space_model_classifier as ssm_clf
+    from framework_extended import state_space_model_linear_gaussian as ssm_lg
+    from framework_extended import state_space_model_mixture as ssm_mix
+
+    import tempfile
+
+    # the reference caches into <package>/tmp, which is read-only here: restarts (fit(use_cache=True) inside the
+    # restart loop, :286-297) would raise in to_pickle and be silently dropped.  Point it at a scratch directory.
+    ssm_mix.home_dir = tempfile.mkdtemp(prefix="mtm_ref_cache_")
+    out = {}
+    rng = np.random.default_rng(909)
+    n_tr, n_te, T, d, l, n_c = 300, 120, 6, 2, 3, 2
+    z, x, lab, comps = sample_mixture(ssm, rng, n_tr + n_te, T, d, l, n_c, 0.15, 1.0)
+    ztr, xtr, zte, xte = z[:, :n_tr].copy(), x[:, :n_tr].copy(), z[:, n_tr:].copy(), x[:, n_tr:].copy()
+    out.update(ztr=ztr, xtr=xtr, zte=zte, xte=xte, lab_tr=lab[:n_tr], lab_te=lab[n_tr:])
+    for tag, kw in (("rand", dict(init="random", n_iter=50, n_restarts=2)), ("km", dict(init="k-means-all", n_iter=50))):
+        zz = ztr if tag == "rand" else np.where(np.isnan(ztr), 0.0, ztr)  # k-means needs finite states
+        mdl = ssm_mix.StateSpaceMixtureModel(n_clusters=n_c, data=(zz, xtr),
+                                             component_model=ssm_lg.StateSpaceLinearGaussian,
+                                             rng=np.random.default_rng(3)).fit(use_cache=False, **kw)
+        pp, pn = mdl.predict_proba(data=(zte, xte), return_prenormalized_log_probs=True)
+        out.update({f"{tag}_assign": np.array(mdl.cluster_assignment), f"{tag}_pi": np.array(mdl.cluster_propensities),
+                    f"{tag}_score": mdl.score(), f"{tag}_mll": mdl.model_log_likelihood(),
+                    f"{tag}_score_te": mdl.score(data=(zte, xte)), f"{tag}_proba_tr": mdl.predict_proba(),
+                    f"{tag}_proba_te": pp, f"{tag}_prenorm_te": pn,
+                    f"{tag}_pred_te": mdl.predict(data=(zte, xte), letters=False),
+                    f"{tag}_index_te": mdl.cluster_assignment_index(cluster="B", data=(zte, xte)),
+                    f"{tag}_A0": mdl.cluster_models[0].state_model["coeff"]})
+    clf = ssm_clf.StateSpaceModelClassifier(component_model=ssm_lg.StateSpaceLinearGaussian).fit(
+        data=(ztr, xtr), labels=lab[:n_tr])
+    out.update(clf_score=clf.score(), clf_score_te=clf.score(data=(zte, xte)), clf_proba_te=clf.predict_proba((zte, xte)),
+               clf_pred_te=clf.predict((zte, xte)), clf_pred_tr=clf.predict())
+    np.savez_compressed(os.path.join(HERE, "extended.npz"), **out)
+    print("extended.npz written; scores", out["rand_score"], out["km_score"], out["clf_score"])
+
+
 if __name__ == "__main__":
     ssm, mmm, uss = import_reference()
+    if "ext" in (sys.argv[1:] or ["ext"]):
+        golden_extended(ssm)
     which = sys.argv[1:] or ["ssm", "em", "restarts", "adni", "lg", "pred"]
     if "pred" in which:
         golden_predictors(ssm, mmm)

@@ -661,3 +661,37 @@ def test_full_size_properties(eng):
     llo = oc.seq_loglik_matrix(P, sub.z.cpu().numpy(), sub.x.cpu().numpy())
     assert relerr(r["ll"].cpu().numpy(), llo) < RTOL
     assert np.array_equal(r["assign"].cpu().numpy(), oc.assign(llo, P[:, 0]))
+
+
+def test_extended_mixture_and_classifier(g_ext, tmp_path):
+    """framework_extended's StateSpaceMixtureModel and StateSpaceModelClassifier with linear-Gaussian
+    components against the reference's own fits (random start with restarts, k-means-all start) and predictions."""
+    import mtm_b200  # noqa: F401
+    from mtm_b200.framework_extended import state_space_model_classifier as xc
+    from mtm_b200.framework_extended import state_space_model_linear_gaussian as xl
+    from mtm_b200.framework_extended import state_space_model_mixture as xm
+
+    g = g_ext
+    xm.home_dir = str(tmp_path)  # restarts go through the cache like the reference's (scratch directory)
+    ztr, xtr, zte, xte = g["ztr"], g["xtr"], g["zte"], g["xte"]
+    for tag, kw in (("rand", dict(init="random", n_iter=50, n_restarts=2)), ("km", dict(init="k-means-all", n_iter=50))):
+        zz = ztr if tag == "rand" else np.where(np.isnan(ztr), 0.0, ztr)
+        mdl = xm.StateSpaceMixtureModel(n_clusters=2, data=(zz, xtr), component_model=xl.StateSpaceLinearGaussian,
+                                        rng=np.random.default_rng(3)).fit(use_cache=False, **kw)
+        assert np.array_equal(mdl.cluster_assignment, g[f"{tag}_assign"]), tag
+        assert relerr(mdl.cluster_propensities, g[f"{tag}_pi"]) < RTOL
+        assert relerr(mdl.cluster_models[0].state_model["coeff"], g[f"{tag}_A0"]) < RTOL
+        assert abs(mdl.score() - float(g[f"{tag}_score"])) < RTOL * abs(float(g[f"{tag}_score"]))
+        assert abs(mdl.model_log_likelihood() - float(g[f"{tag}_mll"])) < RTOL * abs(float(g[f"{tag}_mll"]))
+        assert abs(mdl.score(data=(zte, xte)) - float(g[f"{tag}_score_te"])) < RTOL * abs(float(g[f"{tag}_score_te"]))
+        assert relerr(mdl.predict_proba(), g[f"{tag}_proba_tr"]) < RTOL
+        pp, pn = mdl.predict_proba(data=(zte, xte), return_prenormalized_log_probs=True)
+        assert relerr(pp, g[f"{tag}_proba_te"]) < RTOL and relerr(pn, g[f"{tag}_prenorm_te"]) < RTOL
+        assert np.array_equal(mdl.predict(data=(zte, xte), letters=False), g[f"{tag}_pred_te"])
+        assert relerr(mdl.cluster_assignment_index(cluster="B", data=(zte, xte)), g[f"{tag}_index_te"]) < RTOL
+    clf = xc.StateSpaceModelClassifier(component_model=xl.StateSpaceLinearGaussian).fit(data=(ztr, xtr), labels=g["lab_tr"])
+    assert abs(clf.score() - float(g["clf_score"])) < RTOL * abs(float(g["clf_score"]))
+    assert abs(clf.score(data=(zte, xte)) - float(g["clf_score_te"])) < RTOL * abs(float(g["clf_score_te"]))
+    assert relerr(clf.predict_proba((zte, xte)), g["clf_proba_te"]) < RTOL
+    assert np.array_equal(clf.predict((zte, xte)), g["clf_pred_te"])
+    assert np.array_equal(clf.predict(), g["clf_pred_tr"])
