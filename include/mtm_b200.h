@@ -220,6 +220,9 @@ int mtm_sweep_fit(mtm_handle *h, int n_c, int n_restarts, double alpha, int n_st
  * mtm_mstep, mtm_em_fit, mtm_score, mtm_comm_destroy. */
 int mtm_comm_unique_id(void *id128_out);
 int mtm_comm_init(mtm_handle *h, const void *id128, int world_size, int rank);
+/* alternative to mtm_comm_init: use a communicator the caller already owns (an ncclComm_t of the same NCCL
+ * library, world_size ranks, this process = rank).  The caller keeps ownership; mtm_comm_destroy only detaches. */
+int mtm_comm_attach(mtm_handle *h, void *nccl_comm, int world_size, int rank);
 int mtm_comm_destroy(mtm_handle *h);
 /* Optional, after mtm_comm_init: replace the per-iteration ncclAllReduce of the statistics (6.8 KB at n_c = 8,
  * latency-bound) by a one-shot all-reduce over NVLink peer memory — every rank stores its vector into every

@@ -72,6 +72,7 @@ SIGNATURES = {
                            ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_i64), _i]),
     "mtm_comm_unique_id": (_i, [_vp]),
     "mtm_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "mtm_comm_attach": (_i, [_vp, _vp, _i, _i]),
     "mtm_comm_destroy": (_i, [_vp]),
     "mtm_p2p_export": (_i, [_vp, _vp]),
     "mtm_p2p_attach": (_i, [_vp, _vp, _i, _i]),

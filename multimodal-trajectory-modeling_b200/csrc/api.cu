@@ -91,6 +91,7 @@ struct mtm_handle {
     cudaEvent_t ev_free = nullptr;       // staging buffers free again (previous step finished)
     bool stream_ready = false;
     ncclComm_t comm = nullptr;
+    bool comm_owned = true;  // created by mtm_comm_init (destroyed with the handle) or attached by the caller
     int world = 1, rank = 0;
     // peer-memory all-reduce (p2p.cu)
     P2PView p2p{};
@@ -393,7 +394,7 @@ int mtm_create(int device, void *stream, mtm_handle **out) {
 int mtm_destroy(mtm_handle *h) {
     if (!h) return 0;
     DeviceGuard g(h->device);
-    if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+    if (h->comm && h->comm_owned && g_nccl.ok) g_nccl.CommDestroy(h->comm);
     if (h->stream_ready) {
         for (int k = 0; k < 64; ++k) {
             cudaEventDestroy(h->ev_up[k]);
@@ -857,6 +858,20 @@ int mtm_comm_init(mtm_handle *h, const void *id128, int world_size, int rank) {
         h->comm = nullptr;
         return fail(h, -3, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
     }
+    h->comm_owned = true;
+    h->world = world_size;
+    h->rank = rank;
+    return 0;
+}
+
+int mtm_comm_attach(mtm_handle *h, void *nccl_comm, int world_size, int rank) {
+    if (!h || !nccl_comm) return -1;
+    if (world_size < 1 || rank < 0 || rank >= world_size) return fail(h, -1, "bad world_size / rank");
+    std::string err;
+    if (!load_nccl(err)) return fail(h, -3, "%s", err.c_str());
+    if (h->comm) return fail(h, -1, "a communicator is already attached");
+    h->comm = static_cast<ncclComm_t>(nccl_comm);
+    h->comm_owned = false;  // the caller keeps ownership: mtm_comm_destroy only detaches it
     h->world = world_size;
     h->rank = rank;
     return 0;
@@ -921,8 +936,9 @@ int mtm_comm_destroy(mtm_handle *h) {
     if (h->comm && g_nccl.ok) {
         DeviceGuard g(h->device);
         cudaStreamSynchronize(h->stream);
-        g_nccl.CommDestroy(h->comm);
+        if (h->comm_owned) g_nccl.CommDestroy(h->comm);
     }
+    h->comm_owned = true;
     h->comm = nullptr;
     h->world = 1;
     h->rank = 0;
