@@ -216,7 +216,7 @@ __device__ __forceinline__ void filter_condition_z(const DM &dm, FilterState<DM>
             const double r = obs ? fast_rcp(s) : 0.0;
             const double v = obs ? (y - f.mu[j]) : 0.0;
             f.q = fma(v * v, r, f.q);
-            f.mant *= obs ? s : 1.0;
+            if (obs) f.mant *= s;  // predicated DMUL (a select against 1.0 costs four IMAD moves, which steal FP64 issue slots)
             f.k += obs ? 1 : 0;
             double col[DM::DM];
             MTM_UNROLL
@@ -310,7 +310,7 @@ __device__ __forceinline__ void filter_condition_x(const DM &dm, FilterState<DM>
             const double r = obs ? fast_rcp(s) : 0.0;
             const double v = obs ? (y - mux[j]) : 0.0;
             f.q = fma(v * v, r, f.q);
-            f.mant *= obs ? s : 1.0;
+            if (obs) f.mant *= s;  // predicated DMUL (a select against 1.0 costs four IMAD moves, which steal FP64 issue slots)
             f.k += obs ? 1 : 0;
             MTM_UNROLL
             for (int i = 0; i < DM::DM; ++i) {
@@ -411,7 +411,7 @@ __device__ __forceinline__ void filter_condition_x_point(const DM &dm, FilterSta
             const double r = obs ? fast_rcp(s) : 0.0;
             const double v = obs ? (y - mux[j]) : 0.0;
             f.q = fma(v * v, r, f.q);
-            f.mant *= obs ? s : 1.0;
+            if (obs) f.mant *= s;  // predicated DMUL (a select against 1.0 costs four IMAD moves, which steal FP64 issue slots)
             f.k += obs ? 1 : 0;
             MTM_UNROLL
             for (int a = j + 1; a < DM::LM; ++a) {

@@ -8,5 +8,5 @@ mkdir -p ../../tools/variants _build_var
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 $NVCC $ARCH -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall -ccbin /usr/bin/g++ -DMTM_ONLY_44 "$@" -c estep.cu -o _build_var/estep_$name.o
-$NVCC $ARCH -shared -o ../../tools/variants/libmtm_$name.so _build_var/estep_$name.o _build/api.o _build/mstep.o _build/peak.o _build/rng.o _build/p2p.o _build/order.o -ldl
+$NVCC $ARCH -shared -o ../../tools/variants/libmtm_$name.so _build_var/estep_$name.o $(ls _build/*.o | grep -v "/estep.o") -ldl
 echo built libmtm_$name.so
