@@ -415,7 +415,10 @@ def main():
                 "flops_per_eval_executed": f_eval - f_skip,
                 "frac_executed": (f_eval - f_skip) * evals_launch / (ms_e * 1e-3) * 1e-12 / fp64_peak,
                 "point_steps_per_trajectory": n_point,
-                "peak_source": "measured here: mtm_fp64_peak DFMA micro-kernel, best of 10 (nominal 37.2)",
+                "peak_source": "measured here: mtm_fp64_peak, the better of two DFMA micro-kernels, best of 10 each "
+                               "(nominal 37.2; the same instruction stream as a stand-alone probe on an idle device: "
+                               "36.0-36.9, profiles/r1p_mix_probe.txt)",
+                "frac_of_nominal": achieved_tf / 37.2,
                 "achieved_survey_formula": f_survey * evals_launch / (ms_e * 1e-3) * 1e-12,
                 "hbm": {"achieved": bpt * n_loc / (ms_e * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bpt * n_loc / (ms_e * 1e-3) * 1e-9 / hbm_peak, "bytes_per_trajectory": bpt,

@@ -1043,7 +1043,7 @@ int mtm_fp64_peak(mtm_handle *h, int reps, double *tflops_out) {
     if (!h || !tflops_out) return -1;
     DeviceGuard g(h->device);
     MTM_CUDA(h, run_fp64_peak(reps < 1 ? 1 : reps, h->sm_count, h->stream, tflops_out));
-    h->launches += (reps < 1 ? 1 : reps) + 2;
+    h->launches += 2 * ((reps < 1 ? 1 : reps) + 2);
     return 0;
 }
 
