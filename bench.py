@@ -438,8 +438,14 @@ def main():
         ll = r["ll"].cpu().numpy()
         with np.errstate(all="ignore"):
             err = float(np.nanmax(np.abs(ll - llo) / np.maximum(1.0, np.abs(llo))))
+        with np.errstate(all="ignore"):
+            pren = np.sort(np.log(P[:, :1]) + llo, axis=0)  # log pi_c + ll_c, ascending over clusters
+            margin = float(np.nanmin(pren[-1] - pren[-2])) if cfg["n_c"] > 1 else None
         parity = {"trajectories": npre, "max_rel_ll_err": err,
-                  "assignments_equal": bool(np.array_equal(r["assign"].cpu().numpy(), oc.assign(llo, P[:, 0])))}
+                  "assignments_equal": bool(np.array_equal(r["assign"].cpu().numpy(), oc.assign(llo, P[:, 0]))),
+                  # smallest gap between the best and the second-best cluster of a trajectory (log domain): how
+                  # far the closest call in the sample is from a tie that rounding could flip
+                  "min_top2_margin": margin}
 
     # ---- end to end: host buffers in, labels + parameters out, copies inside the timed region ----
     e2e = None
