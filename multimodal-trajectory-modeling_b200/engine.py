@@ -317,6 +317,11 @@ class Engine:
         self._chk(self.lib.mtm_comm_init(self.h, buf, world, rank))
         self.world, self.rank = world, rank
 
+    def comm_attach(self, nccl_comm: int, world: int, rank: int):
+        """Use a communicator the caller owns (an ncclComm_t as an integer address); see mtm_comm_attach."""
+        self._chk(self.lib.mtm_comm_attach(self.h, ctypes.c_void_p(nccl_comm), world, rank))
+        self.world, self.rank = world, rank
+
     def p2p_export(self) -> bytes:
         buf = ctypes.create_string_buffer(64)
         self._chk(self.lib.mtm_p2p_export(self.h, buf))

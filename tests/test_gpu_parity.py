@@ -695,3 +695,38 @@ def test_extended_mixture_and_classifier(g_ext, tmp_path):
     assert relerr(clf.predict_proba((zte, xte)), g["clf_proba_te"]) < RTOL
     assert np.array_equal(clf.predict((zte, xte)), g["clf_pred_te"])
     assert np.array_equal(clf.predict(), g["clf_pred_tr"])
+
+
+def test_comm_attach_caller_owned_communicator(eng, g_em):
+    """mtm_comm_attach: a caller-owned ncclComm_t (created here straight from libnccl, world size 1) carries the
+    per-iteration all-reduce; the fit equals the golden trace, and detaching leaves the communicator alive."""
+    import ctypes
+
+    import mtm_b200
+
+    nccl = ctypes.CDLL("libnccl.so.2")
+    uid = ctypes.create_string_buffer(128)
+    assert nccl.ncclGetUniqueId(uid) == 0
+
+    class Uid(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_char * 128)]
+
+    comm = ctypes.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, Uid, ctypes.c_int]
+    assert nccl.ncclCommInitRank(ctypes.byref(comm), 1, Uid.from_buffer_copy(uid.raw), 0) == 0
+    try:
+        eng.comm_attach(comm.value, 1, 0)
+        c = _case(g_em, "c2s")
+        data = mtm_b200.DeviceData(c["z"], c["x"], eng.device, pattern_order=True)
+        assign = data.to_resident(g_em["c2s_assign0"].astype(np.int32))
+        params, info = eng.em_fit(data, assign, c["n_c"], c["alpha"], c["n_steps"])
+        assert info["switches"] == list(g_em["c2s_switches"])
+        assert np.array_equal(data.from_resident(assign).cpu().numpy(), g_em["c2s_assign"])
+        assert relerr(params.cpu().numpy(), g_em["c2s_params"]) < RTOL
+    finally:
+        eng.comm_destroy()  # detaches only: the communicator is still the caller's
+    count = ctypes.c_int(0)
+    nccl.ncclCommCount.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+    assert nccl.ncclCommCount(comm, ctypes.byref(count)) == 0 and count.value == 1
+    nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+    assert nccl.ncclCommDestroy(comm) == 0
