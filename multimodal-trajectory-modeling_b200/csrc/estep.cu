@@ -11,8 +11,10 @@
 // Memory: for a fixed time step the 32 lanes of a warp read 32 consecutive trajectories, i.e.
 // 32*d*8 contiguous bytes of z and 32*l*8 of x (16-byte vector loads, read-only path).  A
 // trajectory is streamed from HBM once per E-step: the n_c-1 later cluster passes of the same
-// thread hit L1/L2.  Parameters (n_c x 85 doubles at d=l=4) sit in shared memory and are read
-// as warp-uniform broadcasts.
+// thread hit L1/L2.  Parameters (n_c x 85 doubles at d=l=4) sit in the constant bank and reach the
+// DFMAs as uniform-register operands (CONSTP; shared memory when they do not fit or for run-time
+// dimensions).  With the resident set in pattern order (order.cu) whole warps take the point-mass
+// shortcut of filter.cuh in the steps whose hidden state is completely present.
 #include <cstdlib>
 
 #include "common.cuh"
