@@ -233,12 +233,14 @@ size_t estep_smem(int n_c, int T0, int d, int l, bool fused) {
 
 int estep_grid(int64_t n, int sm_count, bool fused) {
     const int64_t tiles = (n + kEThreads - 1) / kEThreads;
-    // Static tile striding (uniform cost per tile), blocks = a multiple of the SM count.  Plain E-step:
-    // 32 per SM.  Fused: every block also carries n_c*106 double-double accumulators that a reduction has
-    // to read back, which argues for few blocks — but measured at 10 M x 8 (profiles/r1h_grid_sweep.txt)
-    // 3 / 6 / 12 / 24 / 64 blocks per SM give 23.8 / 23.0 / 22.4 / 22.1 / 22.0 ms: many short-lived blocks
-    // de-phase the statistics epilogues of the co-resident blocks.  24 per SM (48 MB of partials at n_c = 8).
-    int per_sm = fused ? 24 : 32;
+    // Static tile striding (uniform cost per tile), blocks = a multiple of the SM count and of the 3 resident
+    // blocks per SM.  Plain E-step: 32 per SM (30 / 36 / 48 measure the same).  Fused: every block also carries
+    // n_c*106 double-double accumulators that a reduction has to read back, which argues for few blocks — but many
+    // short-lived blocks de-phase the statistics epilogues of the co-resident blocks: at 10 M x 8 on the
+    // pattern-ordered set 12 / 18 / 24 / 36 / 48 / 72 blocks per SM give 18.53 / 18.35 / 18.19 / 18.09 / 18.10 /
+    // 18.08 ms (first build: 3 / 6 / 12 / 24 / 64 -> 23.8 / 23.0 / 22.4 / 22.1 / 22.0, profiles/r1h_grid_sweep.txt).
+    // 36 per SM (72 MB of partials at n_c = 8).
+    int per_sm = fused ? 36 : 32;
     if (const char *e = getenv(fused ? "MTM_FUSED_BLOCKS_PER_SM" : "MTM_ESTEP_BLOCKS_PER_SM")) {  // tuning knob
         const int v = atoi(e);
         if (v > 0) per_sm = v;
