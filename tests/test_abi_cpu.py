@@ -161,3 +161,22 @@ def test_import_as_reference_package_name():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0, out.stderr[-800:]
     assert out.stdout.split()[0] == "framework.marginalizable_mixture_model" and "(12,)" in out.stdout
+
+
+def test_extended_host_helpers():
+    """framework_extended host-side pieces that need no GPU: take_finite_along_axis (the example of
+    util_state_space.py:353-363) and the constructor's bookkeeping of StateSpaceMixtureModel."""
+    import mtm_b200  # noqa: F401
+    from mtm_b200.framework_extended import state_space_model_linear_gaussian as xl
+    from mtm_b200.framework_extended import state_space_model_mixture as xm
+
+    eg = np.concatenate([np.arange(7), np.repeat(np.nan, 3), np.arange(2)]).reshape(6, 2)
+    assert np.array_equal(xm.take_finite_along_axis(eg, axis=0), np.array([[0.0, 1.0], [2.0, 3.0], [4.0, 5.0], [0.0, 1.0]]))
+    rng = np.random.default_rng(0)
+    z, x = rng.normal(size=(3, 20, 2)), rng.normal(size=(3, 20, 1))
+    m = xm.StateSpaceMixtureModel(n_clusters=3, data=(z, x), component_model=xl.StateSpaceLinearGaussian,
+                                  rng=np.random.default_rng(7))
+    assert (m.n_timesteps, m.n_data, m.d_states, m.d_observations) == (3, 20, 2, 1)
+    assert np.array_equal(m.cluster_assignment, np.random.default_rng(7).integers(3, size=20))
+    assert m.correspondence == {0: "A", 1: "B", 2: "C"} and m.inverse_correspondence["B"] == 1
+    assert np.allclose(m.cluster_propensities, 1 / 3) and len(m.cluster_models) == 3 and len(m.hex_hash) == 32
