@@ -402,10 +402,10 @@ def main():
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-                # (profiles/r1n_fused_ncu_summary.md: 1.0331 GB + 55.3 MB for 2 M trajectories = 544.2 B per
-                # trajectory: 517 B read = one pass over the data + labels, 27.7 B written = labels + block partials),
+                # (profiles/r1s_fused_ncu_summary.md: 1.0349 GB + 76.2 MB for 2 M trajectories = 555.5 B per
+                # trajectory: 517 B read = one pass over the data + labels, 38 B written = labels + block partials),
                 # scaled to this launch's trajectory count
-                "traffic": 544.2 * n_loc, "traffic_unit": "bytes per launch (ncu-measured 544.2 B/trajectory x n)",
+                "traffic": 555.5 * n_loc, "traffic_unit": "bytes per launch (ncu-measured 555.5 B/trajectory x n)",
                 "kernel": "estep_kernel<4,4,HAS_Z,CONSTP,FUSE> (E-step + fused M-step statistics; the timed span also "
                           "holds the two ~10 us reduction kernels and, for N > 1, the all-reduce)",
                 "kernel_ms": ms_e,
