@@ -100,6 +100,8 @@ struct mtm_handle {
     void *p2p_mapped[kMaxPeers] = {};  // peers' mailboxes opened here
     unsigned int *p2p_counter = nullptr;
     unsigned int p2p_seq = 0;
+    long long *d_rng = nullptr;  // mtm_random_labels: rejection list [kRngCap] + counter, allocated on first use
+    long long *h_rng = nullptr;  // pinned mirror
     std::string err;
     int64_t launches = 0;
 };
@@ -238,11 +240,11 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
 
 constexpr int kP2PCap = 16384;  // doubles per rank and parity in a mailbox (128 KB): n_c * 106 + 2 fits for n_c <= 64
 
-int allreduce_stats(mtm_handle *h, double *buf, size_t count) {
+int allreduce_stats(mtm_handle *h, double *buf, size_t count, int R = 1) {
     if (!h->comm) return 0;
     if (h->p2p_on && count <= (size_t)kP2PCap) {
         h->p2p_seq += 1;
-        MTM_CUDA(h, launch_p2p_allreduce(buf, (int)count, h->p2p, h->p2p_seq, h->p2p_counter, h->d_ctrl, h->stream));
+        MTM_CUDA(h, launch_p2p_allreduce(buf, (int)count, h->p2p, h->p2p_seq, h->p2p_counter, h->d_ctrl, R, h->stream));
         h->launches += 2;
         return 0;
     }
@@ -256,12 +258,12 @@ int allreduce_stats(mtm_handle *h, double *buf, size_t count) {
 int enqueue_stats_reduce(mtm_handle *h, int n_c, int grid, int check_done, int with_switches, int R = 1) {
     const mtm_data &dt = h->data;
     const int n_vals = n_c * stats_stride(dt.d, dt.l);
-    if (int rc = ensure(h, h->d_statsbuf, h->statsbuf_cap, ((size_t)n_vals + 2) * R)) return rc;
+    if (int rc = ensure(h, h->d_statsbuf, h->statsbuf_cap, ((size_t)n_vals + kTail) * R)) return rc;
     MTM_CUDA(h, launch_stats_reduce(h->d_partials, grid, n_vals, h->d_statsbuf,
                                     h->d_partials + 2 * (size_t)R * grid * n_vals, h->d_ctrl, check_done,
                                     with_switches, (double)dt.n, R, h->stream));
     h->launches += 2;
-    return allreduce_stats(h, h->d_statsbuf, ((size_t)n_vals + 2) * R);
+    return allreduce_stats(h, h->d_statsbuf, ((size_t)n_vals + kTail) * R, R);
 }
 
 // statistics of the resident set under `assign` (stand-alone kernel) + reduce + all-reduce
@@ -404,6 +406,12 @@ int mtm_destroy(mtm_handle *h) {
         cudaStreamDestroy(h->copy_stream);
         cudaStreamDestroy(h->down_stream);
     }
+    for (int q = 0; q < kMaxPeers; ++q)
+        if (h->p2p_mapped[q]) cudaIpcCloseMemHandle(h->p2p_mapped[q]);
+    cudaFree(h->p2p_mailbox);
+    cudaFree(h->p2p_counter);
+    cudaFree(h->d_rng);
+    cudaFreeHost(h->h_rng);
     cudaFree(h->d_ctrl);
     cudaFreeHost(h->h_ctrl);
     cudaFree(h->d_partials);
@@ -828,7 +836,7 @@ int mtm_sweep_fit(mtm_handle *h, int n_c, int n_restarts, double alpha, int n_st
             return rc;
         MTM_CUDA(h, launch_score_reduce(h->d_score + 2 * R, grid, h->d_score, R, h->stream));
         h->launches += 1;
-        if (int rc = allreduce_stats(h, h->d_score, (size_t)2 * R)) return rc;
+        if (int rc = allreduce_stats(h, h->d_score, (size_t)2 * R, R)) return rc;
         MTM_CUDA(h, cudaMemcpyAsync(scores_host, h->d_score, sizeof(double) * 2 * R, cudaMemcpyDeviceToHost, h->stream));
         if (int rc = read_ctrl(h, R)) return rc;
         if (score_status_host)
@@ -919,7 +927,15 @@ int mtm_p2p_attach(mtm_handle *h, const void *handles_all, int world_size, int r
     h->p2p.world = world_size;
     h->p2p.rank = rank;
     h->p2p.cap = kP2PCap;
-    h->p2p_seq = 0;
+    double timeout_s = 60.0;
+    if (const char *e = getenv("MTM_B200_P2P_TIMEOUT_S")) {
+        const double v = atof(e);
+        if (v > 0.0) timeout_s = v;
+    }
+    h->p2p.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    // p2p_seq is NOT reset: the mailbox (and the sequence numbers left in its flags) outlives a detach, so the
+    // counter stays monotonic per handle.  All ranks attach, exchange and detach together (collective calls), hence
+    // their counters agree; a restart from 1 would match the stale flags of an earlier session at once.
     h->p2p_on = true;
     return 0;
 }
@@ -954,16 +970,15 @@ int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64
     if (n_c < 1 || n < 1) return fail(h, -1, "bad arguments");
     DeviceGuard g(h->device);
     constexpr int kCap = 4096;
-    long long *d_list = nullptr;
-    int *d_cnt = nullptr;
-    MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&d_list), sizeof(long long) * kCap + sizeof(int)));
-    struct Free {  // scratch is released on every exit path
-        void *p;
-        ~Free() { cudaFree(p); }
-    } free_list{d_list};
-    d_cnt = reinterpret_cast<int *>(d_list + kCap);
+    // scratch lives with the handle (one call per restart at scale); every copy is stream-ordered with the kernels
+    if (!h->d_rng) {
+        MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->d_rng), sizeof(long long) * (kCap + 1)));
+        MTM_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_rng), sizeof(long long) * (kCap + 1)));
+    }
+    long long *d_list = h->d_rng, *h_list = h->h_rng;
+    int *d_cnt = reinterpret_cast<int *>(d_list + kCap);
+    int *h_cnt = reinterpret_cast<int *>(h_list + kCap);
     unsigned long long st[4] = {pcg_state[0], pcg_state[1], pcg_state[2], pcg_state[3]};
-    long long h_list[kCap];
     int n_rej = 0;
     if (n_c > 1) {
         // The first n + slack draws cover the n accepted ones as long as fewer than `slack` of them are rejected;
@@ -973,14 +988,16 @@ int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64
             MTM_CUDA(h, cudaMemsetAsync(d_cnt, 0, sizeof(int), h->stream));
             MTM_CUDA(h, launch_rng_reject(st, (unsigned int)n_c, n + slack, d_list, kCap, d_cnt, h->stream));
             h->launches += 1;
-            MTM_CUDA(h, cudaMemcpyAsync(&n_rej, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            MTM_CUDA(h, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+            n_rej = *h_cnt;
             if (n_rej > kCap) return fail(h, -1, "more than %d rejected draws: n too large for this n_c", kCap);
             if (n_rej < slack) break;
             slack = 2 * (long long)n_rej + 64;
         }
         if (n_rej > 0) {
-            MTM_CUDA(h, cudaMemcpy(h_list, d_list, sizeof(long long) * n_rej, cudaMemcpyDeviceToHost));
+            MTM_CUDA(h, cudaMemcpyAsync(h_list, d_list, sizeof(long long) * n_rej, cudaMemcpyDeviceToHost, h->stream));
+            MTM_CUDA(h, cudaStreamSynchronize(h->stream));
             for (int a = 1; a < n_rej; ++a) {  // insertion sort: a handful of entries
                 const long long v = h_list[a];
                 int b = a - 1;
@@ -990,11 +1007,12 @@ int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64
                 }
                 h_list[b + 1] = v;
             }
-            MTM_CUDA(h, cudaMemcpy(d_list, h_list, sizeof(long long) * n_rej, cudaMemcpyHostToDevice));
+            MTM_CUDA(h, cudaMemcpyAsync(d_list, h_list, sizeof(long long) * n_rej, cudaMemcpyHostToDevice, h->stream));
         }
     }
     MTM_CUDA(h, launch_rng_emit(st, (unsigned int)n_c, n, d_list, n_rej, assign_dev, h->stream));
     h->launches += 1;
+    // the pinned list may be rewritten by the next call: wait for the upload (and the kernel) to finish
     MTM_CUDA(h, cudaStreamSynchronize(h->stream));
     if (n_rejected_host) *n_rejected_host = n_rej;
     return 0;

@@ -70,7 +70,7 @@ struct FinalizeArgs {
     int mode;  // 0: plain M-step (always write); 1: EM-loop step (decide converged / guard / continue)
     int n_steps;
     long long *switch_hist;  // nullable; (R, n_steps)
-    int R;                   // batched restarts: one block per restart; stats (R, n_vals + 2), params (R, n_c, pstride)
+    int R;                   // batched restarts: one block per restart; stats (R, n_vals + kTail), params (R, n_c, pstride)
 };
 
 // peer-memory mailboxes of the one-shot all-reduce (p2p.cu); at most 16 ranks (one NVSwitch box)
@@ -79,9 +79,10 @@ struct P2PView {
     double *data[kMaxPeers];         // data[q]: rank q's mailbox, mapped here: [2][world][cap] doubles
     unsigned int *flags[kMaxPeers];  // flags[q]: rank q's flags: [2][world]
     int world, rank, cap;
+    unsigned long long timeout_ns;   // how long a gather waits for its peers before MTM_STATUS_COMM_TIMEOUT
 };
 cudaError_t launch_p2p_allreduce(double *buf, int count, const P2PView &v, unsigned int seq, unsigned int *done_counter,
-                                 Ctrl *ctrl, cudaStream_t s);
+                                 Ctrl *ctrl, int R, cudaStream_t s);
 
 // launchers (one translation unit per kernel family so that nvcc can build them in parallel)
 cudaError_t launch_estep(const EStepArgs &a, int grid, size_t smem, cudaStream_t s);
@@ -92,13 +93,17 @@ size_t estep_smem(int n_c, int T0, int d, int l, bool fused);
 cudaError_t launch_stats(const StatsArgs &a, int grid, cudaStream_t s);
 int stats_grid(int64_t n, int sm_count);
 size_t stats_smem(int n_c, int d, int l);
-// out (n_vals + 2): reduced statistics, then [n_switches of the preceding E-step, local n].
+// out (n_vals + kTail): reduced statistics, then the tail that rides through the all-reduce with them:
+//   [n_switches of the preceding E-step | local n | 1 if this rank's E-step raised NONFINITE | ... SINGULAR]
+// (all exact small integers as doubles).  After the all-reduce every rank sees the same switch count, the same
+// total n and the same failure bits, so the control flow of finalize_kernel cannot diverge between ranks.
 // `scratch` holds kReduceSlices * n_vals * 2 doubles (two-stage fixed-order reduction).
 constexpr int kReduceSlices = 64;
+constexpr int kTail = 4;
 cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
                                 const Ctrl *ctrl, int check_done, int with_switches, double n_local, int R,
                                 cudaStream_t s);
-// tail (nullable) = the two trailing slots of the all-reduced statistics buffer
+// tail (nullable) = the kTail trailing slots of the all-reduced statistics buffer
 cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStream_t s);
 cudaError_t launch_counts(const int32_t *assign, int64_t n, int n_c, unsigned long long *counts, cudaStream_t s);
 cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, int R, cudaStream_t s);

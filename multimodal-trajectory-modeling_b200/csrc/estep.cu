@@ -79,9 +79,10 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     double *s_pi = s_logpi + a.n_c;                                       // n_c
     uint32_t *s_fin = reinterpret_cast<uint32_t *>(s_pi + a.n_c);         // n_c * T0
     unsigned int *s_cnt = s_fin + a.n_c * a.T0;                           // n_c
+    unsigned int *s_live = s_cnt + a.n_c;                                 // n_c: any coordinate of the cluster's mean finite
     const bool FUSE = a.stats_partials != nullptr;  // block-uniform
     unsigned char *const stats_base =
-        smem_raw + (((reinterpret_cast<unsigned char *>(s_cnt + a.n_c) - smem_raw) + 15) & ~size_t(15));
+        smem_raw + (((reinterpret_cast<unsigned char *>(s_live + a.n_c) - smem_raw) + 15) & ~size_t(15));
     __shared__ double s_red[2][kEThreads / 32];
     __shared__ unsigned int s_sw;
 
@@ -99,6 +100,9 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
         s_pi[c] = src[0];
         s_logpi[c] = log(src[0]);
         mean_finite_masks(dm, src, a.T0, s_fin + c * a.T0);
+        uint32_t any = 0;
+        for (int t = 0; t < a.T0; ++t) any |= s_fin[c * a.T0 + t];
+        s_live[c] = any;
     }
     __syncthreads();
 
@@ -119,8 +123,16 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
         double best = 0.0, best_ll = 0.0, sum_l = 0.0;
         int arg = 0;
         for (int c = 0; c < a.n_c; ++c) {
-            const double ll = filter_eval<DM, HAS_Z>(dm, z_i, zs, x_i, xs, a.T0, PS::get(s_par, r * a.n_c + c, c, stride),
-                                                     s_fin + c * a.T0, bad, a.tshift);
+            // A dead cluster — its unconditional mean is non-finite at every step (NaN m after an empty
+            // initial-state sample) — has no present coordinate at all: the reference's sub-setting leaves an
+            // empty block and ll = -0.0 (SSM:769-773).  It runs ZERO filter steps (block-uniform trip count; the
+            // empty filter finishes with exactly -0.0): without this such a cluster defeats the point-mass vote
+            // and drags every warp through the slow generic path for nothing.  (A trip count rather than a branch
+            // around the call: the branch made ptxas 12.9 drop the uniform-datapath parameter operands of the
+            // observation-only instantiation.)
+            const double ll = filter_eval<DM, HAS_Z>(dm, z_i, zs, x_i, xs, s_live[c] ? a.T0 : 0,
+                                                     PS::get(s_par, r * a.n_c + c, c, stride), s_fin + c * a.T0, bad,
+                                                     a.tshift);
             const double lc = s_pi[c] * exp(ll);
             if (valid) {
                 if (a.ll) a.ll[(int64_t)c * n + i] = ll;
@@ -227,7 +239,7 @@ __global__ void score_reduce_kernel(const double *__restrict__ partials_all, int
 }
 
 size_t estep_smem(int n_c, int T0, int d, int l, bool fused) {
-    const size_t e = (size_t)n_c * param_stride(d, l) * 8 + (size_t)n_c * 16 + (size_t)n_c * T0 * 4 + (size_t)n_c * 4 + 32;
+    const size_t e = (size_t)n_c * param_stride(d, l) * 8 + (size_t)n_c * 16 + (size_t)n_c * T0 * 4 + (size_t)n_c * 8 + 32;
     return e + (fused ? stats_smem_bytes(n_c, d, l) : 0);
 }
 

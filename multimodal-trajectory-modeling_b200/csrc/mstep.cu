@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(kSThreads) stats_kernel(const StatsArgs a) {
 // Two-stage fixed-order reduction of the per-block (hi, lo) partials.
 //  stage 1: slice s (blockIdx.y) adds blocks s, s + S, s + 2S, ... in that order  -> scratch[s][v]
 //  stage 2: thread v adds the S slices in order                                  -> out[v]
-// tail slots: out[n_vals] = n_switches of the preceding E-step (exact integer as double),
-//             out[n_vals+1] = local n
+// tail slots (kTail, common.cuh): out[n_vals] = n_switches of the preceding E-step (exact integer as double),
+//             out[n_vals+1] = local n, out[n_vals+2..3] = this rank's NONFINITE / SINGULAR flags (0 or 1)
 __global__ void stats_reduce1_kernel(const double *__restrict__ partials_all, int grid, int n_vals,
                                      double *scratch_all, const Ctrl *ctrl, int check_done) {
     const int r = blockIdx.z;  // batched restarts
@@ -95,7 +95,7 @@ __global__ void stats_reduce2_kernel(const double *__restrict__ scratch_all, int
     const int r = blockIdx.y;
     if (check_done && ctrl[r].done) return;
     const double *scratch = scratch_all + 2 * (size_t)r * S * n_vals;
-    double *out = out_all + (size_t)r * (n_vals + 2);
+    double *out = out_all + (size_t)r * (n_vals + kTail);
     const unsigned long long *n_switches_src = with_switches ? &ctrl[r].n_switches : nullptr;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v < n_vals) {
@@ -108,8 +108,11 @@ __global__ void stats_reduce2_kernel(const double *__restrict__ scratch_all, int
         out[v] = hi + lo;
     }
     if (v == 0) {
+        const int st = ctrl[r].status;
         out[n_vals] = n_switches_src ? (double)(*n_switches_src) : 0.0;
         out[n_vals + 1] = n_local;
+        out[n_vals + 2] = (st & MTM_STATUS_NONFINITE) ? 1.0 : 0.0;
+        out[n_vals + 3] = (st & MTM_STATUS_SINGULAR) ? 1.0 : 0.0;
     }
 }
 
@@ -313,7 +316,7 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
     const int d = D_ > 0 ? D_ : a.d, l = D_ > 0 ? L_ : a.l, n_c = a.n_c;
     const int F1 = 1 + d + d * (d + 1) / 2, F2 = 1 + 2 * d + d * (2 * d + 1);
     const int sstride = stats_stride(d, l), pstride = param_stride(d, l);
-    a.stats = a0.stats + (size_t)r * ((size_t)n_c * sstride + (tail0 ? 2 : 0));
+    a.stats = a0.stats + (size_t)r * ((size_t)n_c * sstride + (tail0 ? kTail : 0));
     a.params = a0.params + (size_t)r * n_c * pstride;
     a.switch_hist = a0.switch_hist ? a0.switch_hist + (size_t)r * a.n_steps : nullptr;
     const double *tail = tail0 ? a.stats + (size_t)n_c * sstride : nullptr;
@@ -324,6 +327,12 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
         for (int c = 0; c < n_c; ++c) mn = fmin(mn, a.stats[(size_t)c * sstride]);
         int go = 1;
         s_status = 0;
+        if (tail) {
+            // failure bits of the preceding E-step, summed over the ranks: every rank adopts the union, so that
+            // the decisions below (and the status the host finally sees) are the same everywhere
+            const int st = (tail[2] > 0.0 ? MTM_STATUS_NONFINITE : 0) | (tail[3] > 0.0 ? MTM_STATUS_SINGULAR : 0);
+            if (st) ctrl->status |= st;
+        }
         if (a.mode == 1) {
             const long long sw = (long long)(tail ? tail[0] : 0.0);
             ctrl->min_count = (long long)mn;
@@ -334,9 +343,10 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
                     ctrl->exit_code = MTM_EXIT_GUARD0;
                     go = 0;
                 }
-            } else if (ctrl->status & (MTM_STATUS_NONFINITE | MTM_STATUS_SINGULAR)) {
+            } else if (ctrl->status & (MTM_STATUS_NONFINITE | MTM_STATUS_SINGULAR | MTM_STATUS_COMM_TIMEOUT)) {
                 // the reference's E-step raises LinAlgError here (det/solve on a non-finite or
-                // singular covariance block): stop, the host re-raises
+                // singular covariance block): stop, the host re-raises.  A failed exchange (a peer never
+                // arrived) leaves un-reduced statistics behind: stop as well instead of iterating on them.
                 ctrl->done = 1;
                 ctrl->exit_code = MTM_EXIT_ERROR;
                 go = 0;

@@ -37,16 +37,24 @@ __global__ void p2p_push_kernel(const double *__restrict__ src, int count, P2PVi
     }
 }
 
-__global__ void p2p_gather_kernel(double *__restrict__ dst, int count, P2PView v, unsigned int seq, Ctrl *ctrl) {
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void p2p_gather_kernel(double *__restrict__ dst, int count, P2PView v, unsigned int seq, Ctrl *ctrl, int R) {
     const int parity = seq & 1u;
     __shared__ int s_ok;
     if (threadIdx.x == 0) s_ok = 1;
     __syncthreads();
     if (threadIdx.x < v.world) {
         volatile unsigned int *f = reinterpret_cast<volatile unsigned int *>(&v.flags[v.rank][parity * v.world + threadIdx.x]);
-        long long spins = 0;
+        const unsigned long long t0 = global_ns();
+        unsigned int spins = 0;
         while (*f != seq) {
-            if (++spins > (1LL << 31)) {  // a peer never arrived (seconds): give up loudly instead of hanging
+            // a peer never arrived within the wall-clock budget: give up loudly instead of hanging the device
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > v.timeout_ns) {
                 s_ok = 0;
                 break;
             }
@@ -55,7 +63,9 @@ __global__ void p2p_gather_kernel(double *__restrict__ dst, int count, P2PView v
     __syncthreads();
     __threadfence_system();
     if (!s_ok) {
-        if (threadIdx.x == 0) atomicOr(&ctrl->status, MTM_STATUS_COMM_TIMEOUT);
+        // every fit of a batch learns about it: finalize_kernel stops the loop on this bit (MTM_EXIT_ERROR)
+        if (blockIdx.x == 0)
+            for (int r = threadIdx.x; r < (R > 1 ? R : 1); r += blockDim.x) atomicOr(&ctrl[r].status, MTM_STATUS_COMM_TIMEOUT);
         return;
     }
     const double *mine = v.data[v.rank] + (size_t)parity * v.world * v.cap;
@@ -67,12 +77,12 @@ __global__ void p2p_gather_kernel(double *__restrict__ dst, int count, P2PView v
 }
 
 cudaError_t launch_p2p_allreduce(double *buf, int count, const P2PView &v, unsigned int seq, unsigned int *done_counter,
-                                 Ctrl *ctrl, cudaStream_t s) {
+                                 Ctrl *ctrl, int R, cudaStream_t s) {
     const int threads = 128;
     const int blocks = (count + threads - 1) / threads;
     p2p_push_kernel<<<blocks, threads, 0, s>>>(buf, count, v, seq, done_counter);
     // every block of the gather waits on the flags itself, so any grid size is safe
-    p2p_gather_kernel<<<blocks < 32 ? blocks : 32, threads, 0, s>>>(buf, count, v, seq, ctrl);
+    p2p_gather_kernel<<<blocks < 32 ? blocks : 32, threads, 0, s>>>(buf, count, v, seq, ctrl, R);
     return cudaGetLastError();
 }
 

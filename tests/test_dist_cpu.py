@@ -94,7 +94,7 @@ def _worker(rank, world, port, q):
     n_total = int(buf[-1].item())
     P = finalize_from_stats(buf[:-2].reshape(n_c, stride).numpy(), d, l, n_total, 0.0)
     ref = od.m_step(z, x, g[f"{key}_assign0"], n_c, 0.0).packed()
-    err = float(np.max(np.abs(P - ref) / np.maximum(1.0, np.abs(ref))))
+    err = float(np.max(np.abs(P - ref) / np.maximum(1e-6, np.abs(ref))))
     # gather of ragged label shards
     full = mdist.gather_assignments(torch.from_numpy(a_loc.astype(np.int32)), n, world, rank)
     ok = err < 1e-9 and n_total == n and np.array_equal(full, g[f"{key}_assign0"])

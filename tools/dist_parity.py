@@ -39,7 +39,7 @@ def main():
         params, info = eng.em_fit(data, assign, n_c, alpha, n_steps)
         full = mdist.gather_assignments(data.from_resident(assign), n, world, rank)
         P = params.cpu().numpy()
-        err = float(np.max(np.abs(P - g[f"{key}_params"]) / np.maximum(1.0, np.abs(g[f"{key}_params"]))))
+        err = float(np.max(np.abs(P - g[f"{key}_params"]) / np.maximum(1e-6, np.abs(g[f"{key}_params"]))))
         good = (info["switches"] == list(g[f"{key}_switches"]) and np.array_equal(full, g[f"{key}_assign"])
                 and err < 1e-9)
         # scores are all-reduced too
