@@ -84,6 +84,7 @@ struct mtm_handle {
     long long *d_hist = nullptr;
     int hist_cap = 0;
     double *h_pin = nullptr;  // small pinned scratch (16 doubles)
+    double *h_pin32 = nullptr;  // pinned scratch of ensure_pivot (32 doubles)
     cudaStream_t copy_stream = nullptr;  // private upload stream of the host-streaming path
     cudaStream_t down_stream = nullptr;  // private download stream (PCIe is full duplex)
     cudaEvent_t ev_up[64] = {};          // slab k uploaded
@@ -100,6 +101,12 @@ struct mtm_handle {
     void *p2p_mapped[kMaxPeers] = {};  // peers' mailboxes opened here
     unsigned int *p2p_counter = nullptr;
     unsigned int p2p_seq = 0;
+    // pivot of the resident set: the point the M-step moments are taken about (ensure_pivot)
+    double pivot[2 * MTM_MAX_DIM] = {};
+    bool pivot_valid = false;
+    int pivot_world = 0;
+    double *d_pivot = nullptr;  // [32 sums/counts | scratch]
+    size_t pivot_cap = 0;
     long long *d_rng = nullptr;  // mtm_random_labels: rejection list [kRngCap] + counter, allocated on first use
     long long *h_rng = nullptr;  // pinned mirror
     std::string err;
@@ -212,6 +219,7 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
         const size_t n_vals = (size_t)n_c * stats_stride(dt->d, dt->l);
         if (int rc = ensure(h, h->d_partials, h->partials_cap, 2 * n_vals * ((size_t)grid + kReduceSlices) * R)) return rc;
         a.stats_partials = h->d_partials;
+        memcpy(a.pivot, h->pivot, sizeof(a.pivot));  // valid: the callers of the fused mode ran ensure_pivot
     }
     const size_t smem = estep_smem(n_c, a.T0, a.d, a.l, fused);
     if (smem > 200 * 1024) return fail(h, -1, "E-step shared memory %zu B too large (n_c * T0 too big)", smem);
@@ -253,6 +261,45 @@ int allreduce_stats(mtm_handle *h, double *buf, size_t count, int R = 1) {
     return 0;
 }
 
+// The pivot of the resident set = per-feature mean of its finite entries (over all ranks when a communicator is
+// attached), truncated to 12 mantissa bits.  The M-step statistics are accumulated about it (stats_tile.cuh) and
+// finalize_kernel solves on the centred moments, so data with |mean| >> spread lose no digits (the reference works
+// on the rows themselves, MMM:1194-1199, 1267-1270, and has no such cancellation).  Any common point would give
+// the same parameters up to rounding; what matters is that every rank uses the SAME one, hence: computed lazily at
+// the first statistics pass after mtm_set_data — a collective call on every rank — and, with a communicator,
+// never skipped on local information.  Truncation makes the value insensitive to the summation order (it is the
+// same for every GPU count unless a mean sits on a truncation boundary).
+int ensure_pivot(mtm_handle *h) {
+    const int world = h->comm ? h->world : 1;
+    if (h->pivot_valid && h->pivot_world == world) return 0;
+    const mtm_data &dt = h->data;
+    const size_t need = 32 + pivot_scratch_doubles(h->sm_count);
+    if (int rc = ensure(h, h->d_pivot, h->pivot_cap, need)) return rc;
+    const int64_t ld = dt.ld > 0 ? dt.ld : dt.n;
+    MTM_CUDA(h, launch_pivot_sums(dt.z_dev, dt.n, ld, dt.T, dt.d, h->sm_count, h->d_pivot + 32, h->d_pivot, h->stream));
+    MTM_CUDA(h, launch_pivot_sums(dt.x_dev, dt.n, ld, dt.T, dt.l, h->sm_count, h->d_pivot + 32, h->d_pivot + 16, h->stream));
+    h->launches += 4;
+    if (int rc = allreduce_stats(h, h->d_pivot, 32)) return rc;
+    double host[32];
+    MTM_CUDA(h, cudaMemcpyAsync(h->h_pin32, h->d_pivot, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(host, h->h_pin32, sizeof(host));
+    for (int part = 0; part < 2; ++part) {
+        for (int j = 0; j < MTM_MAX_DIM; ++j) {
+            const double sum = host[16 * part + j], cnt = host[16 * part + MTM_MAX_DIM + j];
+            double v = cnt > 0.0 ? sum / cnt : 0.0;
+            uint64_t bits;
+            memcpy(&bits, &v, 8);
+            bits &= ~((uint64_t(1) << 40) - 1);  // keep sign, exponent and the top 12 mantissa bits
+            memcpy(&v, &bits, 8);
+            h->pivot[MTM_MAX_DIM * part + j] = (v == v && v - v == 0.0) ? v : 0.0;
+        }
+    }
+    h->pivot_valid = true;
+    h->pivot_world = world;
+    return 0;
+}
+
 // block partials in h->d_partials (from `grid` blocks) -> h->d_statsbuf [n_c*sstride | n_switches | n_local],
 // all-reduced over the communicator
 int enqueue_stats_reduce(mtm_handle *h, int n_c, int grid, int check_done, int with_switches, int R = 1) {
@@ -267,8 +314,11 @@ int enqueue_stats_reduce(mtm_handle *h, int n_c, int grid, int check_done, int w
 }
 
 // statistics of the resident set under `assign` (stand-alone kernel) + reduce + all-reduce
-int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done, int with_switches, int R = 1) {
+int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done, int with_switches, int R = 1,
+                  bool raw = false) {
     const mtm_data &dt = h->data;
+    if (!raw)
+        if (int rc = ensure_pivot(h)) return rc;
     const size_t n_vals = (size_t)n_c * stats_stride(dt.d, dt.l);
     const int grid = stats_grid(dt.n, h->sm_count);
     const size_t smem = stats_smem(n_c, dt.d, dt.l);
@@ -290,6 +340,7 @@ int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done,
     s.ctrl = h->d_ctrl;
     s.check_done = check_done;
     s.R = R;
+    if (!raw) memcpy(s.pivot, h->pivot, sizeof(s.pivot));  // raw: plain moments (pivot 0), mtm_mstats
     MTM_CUDA(h, launch_stats(s, grid, h->stream));
     h->launches += 1;
     return enqueue_stats_reduce(h, n_c, grid, check_done, with_switches, R);
@@ -298,6 +349,7 @@ int enqueue_stats(mtm_handle *h, const int32_t *assign, int n_c, int check_done,
 // one EM iteration's kernels: E-step (+ fused statistics when possible) -> reduce -> all-reduce
 int enqueue_e_and_stats(mtm_handle *h, int n_c, const double *params, int32_t *assign, int check_done, int R = 1) {
     const mtm_data &dt = h->data;
+    if (int rc = ensure_pivot(h)) return rc;
     if (can_fuse(&dt, n_c)) {
         int grid = 0;
         if (int rc = enqueue_estep(h, &dt, params, n_c, dt.T, assign, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
@@ -326,6 +378,7 @@ int enqueue_finalize(mtm_handle *h, int n_c, double alpha, double *params, int m
     f.n_steps = n_steps;
     f.switch_hist = h->d_hist;
     f.R = R;
+    memcpy(f.pivot, h->pivot, sizeof(f.pivot));
     MTM_CUDA(h, launch_finalize(f, h->d_statsbuf + (size_t)n_c * stats_stride(dt.d, dt.l), h->stream));
     h->launches += 1;
     return 0;
@@ -383,6 +436,7 @@ int mtm_create(int device, void *stream, mtm_handle **out) {
               cudaMallocHost(reinterpret_cast<void **>(&h->h_counts), sizeof(unsigned long long) * MTM_MAX_CLUSTERS) ==
                   cudaSuccess &&
               cudaMallocHost(reinterpret_cast<void **>(&h->h_pin), sizeof(double) * 16) == cudaSuccess &&
+              cudaMallocHost(reinterpret_cast<void **>(&h->h_pin32), sizeof(double) * 32) == cudaSuccess &&
               cudaMemset(h->d_ctrl, 0, sizeof(Ctrl)) == cudaSuccess;
     if (!ok) {
         const char *msg = cudaGetErrorString(cudaGetLastError());
@@ -412,6 +466,7 @@ int mtm_destroy(mtm_handle *h) {
     cudaFree(h->p2p_counter);
     cudaFree(h->d_rng);
     cudaFreeHost(h->h_rng);
+    cudaFree(h->d_pivot);
     cudaFree(h->d_ctrl);
     cudaFreeHost(h->h_ctrl);
     cudaFree(h->d_partials);
@@ -421,6 +476,7 @@ int mtm_destroy(mtm_handle *h) {
     cudaFreeHost(h->h_counts);
     cudaFree(h->d_hist);
     cudaFreeHost(h->h_pin);
+    cudaFreeHost(h->h_pin32);
     delete h;
     return 0;
 }
@@ -439,6 +495,12 @@ int mtm_set_data(mtm_handle *h, const mtm_data *data) {
     }
     if (int rc = check_dims(h, data, 1)) return rc;
     if (!data->z_dev) return fail(h, -1, "the resident training set needs hidden states (z_dev)");
+    // the pivot (ensure_pivot) survives a re-bind of the very same buffers, but only without a communicator: with
+    // one, every rank must reach the collective of ensure_pivot, so it is never skipped on local information
+    const bool same = h->has_data && !h->comm && h->data.z_dev == data->z_dev && h->data.x_dev == data->x_dev &&
+                      h->data.n == data->n && h->data.T == data->T && h->data.d == data->d && h->data.l == data->l &&
+                      h->data.ld == data->ld;
+    if (!same) h->pivot_valid = false;
     h->data = *data;
     h->has_data = true;
     return 0;
@@ -533,7 +595,7 @@ int mtm_mstats(mtm_handle *h, const int32_t *assign_dev, int n_c, double *stats_
     // local statistics only: temporarily detach the communicator
     ncclComm_t keep = h->comm;
     h->comm = nullptr;
-    const int rc = enqueue_stats(h, assign_dev, n_c, 0, 0);
+    const int rc = enqueue_stats(h, assign_dev, n_c, 0, 0, 1, true);  // plain moments (pivot 0)
     h->comm = keep;
     if (rc) return rc;
     const size_t n_vals = (size_t)n_c * stats_stride(h->data.d, h->data.l);
@@ -641,6 +703,9 @@ int mtm_em_step_host(mtm_handle *h, const double *z_host, const double *x_host, 
     }
     h->data = full;  // reductions and finalise read the dimensions of the resident set
     h->has_data = true;
+    // the data are not on the device yet when the first slab's statistics are taken: plain moments (pivot 0)
+    memset(h->pivot, 0, sizeof(h->pivot));
+    h->pivot_valid = false;
     const int sstride = stats_stride(d, l);
     const size_t n_vals = (size_t)n_c * sstride;
     // slab boundaries on 128-trajectory tiles (16-byte alignment of every slab start follows)
@@ -872,6 +937,13 @@ int mtm_comm_init(mtm_handle *h, const void *id128, int world_size, int rank) {
     h->comm_owned = true;
     h->world = world_size;
     h->rank = rank;
+    h->pivot_valid = false;
+    // first collective of a communicator sets up its channels (observed: ~1.7 s): pay it here, not inside a fit
+    if (int rc = ensure(h, h->d_score, h->score_cap, 8)) return rc;
+    MTM_CUDA(h, cudaMemsetAsync(h->d_score, 0, 8 * sizeof(double), h->stream));
+    const int w = g_nccl.AllReduce(h->d_score, h->d_score, 8, kNcclFloat64, kNcclSum, h->comm, h->stream);
+    if (w != 0) return fail(h, -3, "ncclAllReduce (warm-up) failed: %s", g_nccl.GetErrorString(w));
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -883,6 +955,7 @@ int mtm_comm_attach(mtm_handle *h, void *nccl_comm, int world_size, int rank) {
     if (h->comm) return fail(h, -1, "a communicator is already attached");
     h->comm = static_cast<ncclComm_t>(nccl_comm);
     h->comm_owned = false;  // the caller keeps ownership: mtm_comm_destroy only detaches it
+    h->pivot_valid = false;
     h->world = world_size;
     h->rank = rank;
     return 0;
@@ -961,6 +1034,7 @@ int mtm_comm_destroy(mtm_handle *h) {
     h->comm = nullptr;
     h->world = 1;
     h->rank = 0;
+    h->pivot_valid = false;
     return 0;
 }
 

@@ -45,6 +45,7 @@ struct EStepArgs {
     int tshift;                    // always 0 (see filter_eval): a never-taken uniform branch that fixes the code shape
     double *stats_partials;        // nullable: fused mode — the M-step statistics of the NEW labels are
                                    // accumulated in the same pass: (grid, n_c, sstride, 2) block sums
+    double pivot[2 * MTM_MAX_DIM]; // fused mode: the moments are taken about this point: z - pivot[0..d), x - pivot[8..8+l)
 };
 
 struct StatsArgs {
@@ -58,6 +59,7 @@ struct StatsArgs {
     const Ctrl *ctrl;  // [R]
     int check_done;
     int R;             // batched restarts (gridDim.y); assign is (R, n)
+    double pivot[2 * MTM_MAX_DIM];  // moments are taken about this point: z - pivot[0..d), x - pivot[8..8+l)
 };
 
 struct FinalizeArgs {
@@ -71,6 +73,7 @@ struct FinalizeArgs {
     int n_steps;
     long long *switch_hist;  // nullable; (R, n_steps)
     int R;                   // batched restarts: one block per restart; stats (R, n_vals + kTail), params (R, n_c, pstride)
+    double pivot[2 * MTM_MAX_DIM];  // the point the moments in `stats` were taken about (zeros = raw moments)
 };
 
 // peer-memory mailboxes of the one-shot all-reduce (p2p.cu); at most 16 ranks (one NVSwitch box)
@@ -105,6 +108,11 @@ cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, do
                                 cudaStream_t s);
 // tail (nullable) = the kTail trailing slots of the all-reduced statistics buffer
 cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStream_t s);
+// per-feature [sum | count] of the finite entries of a (T, n, w) array: out[0..8) sums, out[8..16) counts;
+// scratch: pivot_scratch_doubles() doubles
+size_t pivot_scratch_doubles(int sm_count);
+cudaError_t launch_pivot_sums(const double *a, int64_t n, int64_t ld, int T, int w, int sm_count, double *scratch,
+                              double *out16, cudaStream_t s);
 cudaError_t launch_counts(const int32_t *assign, int64_t n, int n_c, unsigned long long *counts, cudaStream_t s);
 cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, int R, cudaStream_t s);
 cudaError_t run_fp64_peak(int reps, int sm_count, cudaStream_t s, double *tflops);

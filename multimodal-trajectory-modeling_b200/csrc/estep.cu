@@ -168,7 +168,7 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
                 if ((tid & 31) == 0 && m) atomicAdd(&s_cnt[c], (unsigned int)__popc(m));
             }
         }
-        if (FUSE) stats_tile(dm, a.z, a.x, a.ld, a.T, i, valid ? arg : -1, a.n_c, stats_base);
+        if (FUSE) stats_tile(dm, a.z, a.x, a.ld, a.T, i, valid ? arg : -1, a.n_c, stats_base, a.pivot);
     }
 
     // block epilogue: integer counters by atomics (exact, order-free), fp64 sums in a fixed order

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kSThreads) stats_kernel(const StatsArgs a) {
         const int64_t i_raw = tile * kSThreads + tid;
         const bool valid = i_raw < n;
         const int64_t i = valid ? i_raw : n - 1;
-        stats_tile(dm, a.z, a.x, a.ld, a.T, i, valid ? assign[i] : -1, n_c, smem_raw);
+        stats_tile(dm, a.z, a.x, a.ld, a.T, i, valid ? assign[i] : -1, n_c, smem_raw, a.pivot);
     }
     __syncthreads();
     double *out = a.partials + 2 * ((size_t)r * gridDim.x + blockIdx.x) * n_c * sstride;
@@ -134,12 +134,10 @@ struct RegDims {
     __device__ __forceinline__ int q() const { return kStatic ? Q_ : q_rt; }
 };
 
-// Cholesky solve of (M + alpha I) B = R for SPD M (p x p), R (p x q); M is overwritten by the factor.
-// returns false if a pivot is not positive.
+// Cholesky factor of (M + alpha I) for SPD M (p x p), in place (lower triangle).  false if a pivot is not positive.
 template <class RD>
-__device__ __forceinline__ bool chol_solve(const RD &rd, double (&M)[RD::PM][RD::PM], double (&R)[RD::PM][RD::QM],
-                                           double alpha) {
-    const int p = rd.p(), q = rd.q();
+__device__ __forceinline__ bool chol_factor(const RD &rd, double (&M)[RD::PM][RD::PM], double alpha) {
+    const int p = rd.p();
     bool ok = true;
     MTM_UNROLL
     for (int j = 0; j < RD::PM; ++j) {
@@ -164,41 +162,109 @@ __device__ __forceinline__ bool chol_solve(const RD &rd, double (&M)[RD::PM][RD:
             }
         }
     }
+    return ok;
+}
+
+// v <- (L L')^-1 v with the factor from chol_factor
+template <class RD>
+__device__ __forceinline__ void chol_apply(const RD &rd, const double (&M)[RD::PM][RD::PM], double (&v)[RD::PM]) {
+    const int p = rd.p();
     MTM_UNROLL
-    for (int c = 0; c < RD::QM; ++c) {
-        if (c < q) {
+    for (int i = 0; i < RD::PM; ++i) {
+        if (i < p) {
+            double t = v[i];
             MTM_UNROLL
-            for (int i = 0; i < RD::PM; ++i) {
-                if (i < p) {
-                    double t = R[i][c];
-                    MTM_UNROLL
-                    for (int k = 0; k < RD::PM; ++k)
-                        if (k < i) t -= M[i][k] * R[k][c];
-                    R[i][c] = t / M[i][i];
+            for (int k = 0; k < RD::PM; ++k)
+                if (k < i) t -= M[i][k] * v[k];
+            v[i] = t / M[i][i];
+        }
+    }
+    MTM_UNROLL
+    for (int ii = 0; ii < RD::PM; ++ii) {
+        const int i = RD::PM - 1 - ii;
+        if (i < p) {
+            double t = v[i];
+            MTM_UNROLL
+            for (int k = 0; k < RD::PM; ++k)
+                if (k > i && k < p) t -= M[k][i] * v[k];
+            v[i] = t / M[i][i];
+        }
+    }
+}
+
+// Minimum-norm least squares  B = pinv(G) R  for a symmetric positive SEMI-definite G (p x p, run-time p <= MX)
+// by a cyclic Jacobi eigen-decomposition: what np.linalg.lstsq(X, Y, rcond=-1) (MMM:1194) returns for a
+// rank-deficient design X with G = X'X, R = X'Y.  Eigenvalues below 1e-13 of the largest count as zero (they are
+// rounding noise of the moment matrix; lstsq itself cuts singular values at machine precision).  Run-time indexed
+// arrays in local memory: this is the rare fallback of a ~100-thread kernel.
+__device__ __noinline__ void pinv_solve(int p, int q, double (*G)[MX], double (*R)[MX], double (*B)[MX]) {
+    double V[MX][MX];
+    for (int i = 0; i < p; ++i)
+        for (int j = 0; j < p; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < p; ++i) {
+            diag += G[i][i] * G[i][i];
+            for (int j = i + 1; j < p; ++j) off += G[i][j] * G[i][j];
+        }
+        if (!(off > 1e-40 * diag)) break;
+        for (int a = 0; a < p; ++a) {
+            for (int b = a + 1; b < p; ++b) {
+                const double g = G[a][b];
+                if (g == 0.0) continue;
+                const double theta = (G[b][b] - G[a][a]) / (2.0 * g);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < p; ++k) {  // G <- G J (columns a, b)
+                    const double ga = G[k][a], gb = G[k][b];
+                    G[k][a] = c * ga - sn * gb;
+                    G[k][b] = sn * ga + c * gb;
                 }
-            }
-            MTM_UNROLL
-            for (int ii = 0; ii < RD::PM; ++ii) {
-                const int i = RD::PM - 1 - ii;
-                if (i < p) {
-                    double t = R[i][c];
-                    MTM_UNROLL
-                    for (int k = 0; k < RD::PM; ++k)
-                        if (k > i && k < p) t -= M[k][i] * R[k][c];
-                    R[i][c] = t / M[i][i];
+                for (int k = 0; k < p; ++k) {  // G <- J' G (rows a, b)
+                    const double ga = G[a][k], gb = G[b][k];
+                    G[a][k] = c * ga - sn * gb;
+                    G[b][k] = sn * ga + c * gb;
+                }
+                for (int k = 0; k < p; ++k) {
+                    const double va = V[k][a], vb = V[k][b];
+                    V[k][a] = c * va - sn * vb;
+                    V[k][b] = sn * va + c * vb;
                 }
             }
         }
     }
-    return ok;
+    double lmax = 0.0;
+    for (int i = 0; i < p; ++i) lmax = fmax(lmax, G[i][i]);
+    for (int i = 0; i < p; ++i)
+        for (int c = 0; c < q; ++c) B[i][c] = 0.0;
+    for (int k = 0; k < p; ++k) {
+        const double lam = G[k][k];
+        if (!(lam > 1e-13 * lmax)) continue;
+        for (int c = 0; c < q; ++c) {
+            double t = 0.0;
+            for (int i = 0; i < p; ++i) t += V[i][k] * R[i][c];
+            t /= lam;
+            for (int i = 0; i < p; ++i) B[i][c] += V[i][k] * t;
+        }
+    }
 }
 
-// moments block [cnt | sum v (K) | upper(sum vv')] of v = [a (p) | b (q)] ->
-//   B = argmin |b - a B|^2 + alpha |B|^2 (p x q), Cov = cov(b - a B) with mean removed and N-1
-// (regress / regress_alpha, MMM:1167-1233)
+// moments block [cnt | sum v (K) | upper(sum vv')] of v = [a (p) | b (q)], taken ABOUT THE PIVOT (pa, pb)  ->
+//   B = argmin |b - a B|^2 + alpha |B|^2 (p x q, NO intercept), Cov = cov(b - a B) with mean removed and N-1
+// (regress / regress_alpha, MMM:1167-1233).
+//
+// Everything is done on the scatter about the sample mean, C = sum (v - vbar)(v - vbar)', which the centred
+// moments give without cancellation.  The no-intercept normal equations are a rank-one update of it,
+//   X'X = C_aa + n mu_a mu_a',  X'Y = C_ab + n mu_a mu_b'      (mu = true means = pivot + centred mean),
+// solved with Sherman-Morrison on the factor of C_aa + alpha I:
+//   B0 = (C_aa + alpha I)^-1 C_ab,  w = (C_aa + alpha I)^-1 mu_a,  B = B0 + n / (1 + n mu_a'w) * w (mu_b - B0'mu_a)'.
+// The raw moment matrix (condition ~ |mean|^2 / var worse) is never factorised.  Residual scatter:
+//   sum (r - rbar)(r - rbar)' = C_bb - B'C_ab - C_ab'B + B'C_aa B.
+// alpha = 0 and C_aa not positive definite (rank-deficient or underdetermined design): lstsq's minimum-norm
+// solution through pinv_solve on the reconstructed X'X.
 template <class RD>
-__device__ __forceinline__ int regress_from_moments(const RD &rd, const double *blk, double alpha, double *B_out,
-                                                    double *C_out) {
+__device__ __forceinline__ int regress_from_moments(const RD &rd, const double *blk, double alpha, const double *pa,
+                                                    const double *pb, double *B_out, double *C_out) {
     const int p = rd.p(), q = rd.q();
     const int K = p + q;
     constexpr int KM = RD::PM + RD::QM;
@@ -211,7 +277,11 @@ __device__ __forceinline__ int regress_from_moments(const RD &rd, const double *
         for (int k = 0; k < q * q; ++k) C_out[k] = qnan();
         return MTM_STATUS_EMPTY_FIT;
     }
-    double full[KM][KM];
+    double cm[KM];  // centred means
+    MTM_UNROLL
+    for (int a = 0; a < KM; ++a)
+        if (a < K) cm[a] = sv[a] / cnt;
+    double full[KM][KM];  // scatter about the sample mean
     {
         int o = 0;
         MTM_UNROLL
@@ -220,13 +290,22 @@ __device__ __forceinline__ int regress_from_moments(const RD &rd, const double *
                 MTM_UNROLL
                 for (int b = a; b < KM; ++b)
                     if (b < K) {
-                        full[a][b] = up[o + (b - a)];
-                        full[b][a] = up[o + (b - a)];
+                        const double v = fma(-cnt * cm[a], cm[b], up[o + (b - a)]);
+                        full[a][b] = v;
+                        full[b][a] = v;
                     }
                 o += K - a;
             }
         }
     }
+    double mua[RD::PM], mub[RD::QM];  // true means
+    MTM_UNROLL
+    for (int i = 0; i < RD::PM; ++i)
+        if (i < p) mua[i] = pa[i] + cm[i];
+    MTM_UNROLL
+    for (int c = 0; c < RD::QM; ++c)
+        if (c < q) mub[c] = pb[c] + cm[p + c];
+
     double M[RD::PM][RD::PM], B[RD::PM][RD::QM];
     MTM_UNROLL
     for (int i = 0; i < RD::PM; ++i) {
@@ -234,31 +313,72 @@ __device__ __forceinline__ int regress_from_moments(const RD &rd, const double *
             MTM_UNROLL
             for (int j = 0; j < RD::PM; ++j)
                 if (j < p) M[i][j] = full[i][j];
-            MTM_UNROLL
-            for (int c = 0; c < RD::QM; ++c)
-                if (c < q) B[i][c] = full[i][p + c];
         }
     }
-    if (!chol_solve(rd, M, B, alpha)) {
-        status |= MTM_STATUS_CHOL_FAIL;
+    if (chol_factor(rd, M, alpha)) {
+        double w[RD::PM];
+        MTM_UNROLL
+        for (int i = 0; i < RD::PM; ++i)
+            if (i < p) w[i] = mua[i];
+        chol_apply(rd, M, w);
+        double s = 1.0;
+        MTM_UNROLL
+        for (int i = 0; i < RD::PM; ++i)
+            if (i < p) s = fma(cnt * mua[i], w[i], s);
+        const double f = cnt / s;
+        MTM_UNROLL
+        for (int c = 0; c < RD::QM; ++c) {
+            if (c < q) {
+                double col[RD::PM];
+                MTM_UNROLL
+                for (int i = 0; i < RD::PM; ++i)
+                    if (i < p) col[i] = full[i][p + c];
+                chol_apply(rd, M, col);  // column c of B0
+                double e = mub[c];
+                MTM_UNROLL
+                for (int i = 0; i < RD::PM; ++i)
+                    if (i < p) e = fma(-mua[i], col[i], e);
+                MTM_UNROLL
+                for (int i = 0; i < RD::PM; ++i)
+                    if (i < p) B[i][c] = fma(f * w[i], e, col[i]);
+            }
+        }
+    } else if (alpha == 0.0) {
+        // rank-deficient / underdetermined design: minimum-norm solution of the raw normal equations
+        double G[MX][MX], R[MX][MX], Bm[MX][MX];
+        bool fin = true;
+        for (int i = 0; i < p; ++i) {
+            for (int j = 0; j < p; ++j) {
+                G[i][j] = fma(cnt * mua[i], mua[j], full[i][j]);
+                fin = fin && finite_bits(G[i][j]);
+            }
+            for (int c = 0; c < q; ++c) {
+                R[i][c] = fma(cnt * mua[i], mub[c], full[i][p + c]);
+                fin = fin && finite_bits(R[i][c]);
+            }
+        }
+        if (fin) {
+            pinv_solve(p, q, G, R, Bm);
+            MTM_UNROLL
+            for (int i = 0; i < RD::PM; ++i)
+                MTM_UNROLL
+                for (int c = 0; c < RD::QM; ++c)
+                    if (i < p && c < q) B[i][c] = Bm[i][c];
+        } else {
+            status |= MTM_STATUS_CHOL_FAIL;
+            MTM_UNROLL
+            for (int i = 0; i < RD::PM; ++i)
+                MTM_UNROLL
+                for (int c = 0; c < RD::QM; ++c) B[i][c] = qnan();
+        }
+    } else {
+        status |= MTM_STATUS_CHOL_FAIL;  // ridge system not positive definite: non-finite moments
         MTM_UNROLL
         for (int i = 0; i < RD::PM; ++i)
             MTM_UNROLL
             for (int c = 0; c < RD::QM; ++c) B[i][c] = qnan();
     }
-    // mean residual
-    double rbar[RD::QM];
-    MTM_UNROLL
-    for (int c = 0; c < RD::QM; ++c) {
-        if (c < q) {
-            double s = sv[p + c];
-            MTM_UNROLL
-            for (int i = 0; i < RD::PM; ++i)
-                if (i < p) s -= sv[i] * B[i][c];
-            rbar[c] = s / cnt;
-        }
-    }
-    // E = Sxy - Sxx B (zero for least squares up to rounding, alpha B for ridge)
+    // E = C_ab - C_aa B (zero for least squares up to rounding)
     double E[RD::PM][RD::QM];
     MTM_UNROLL
     for (int i = 0; i < RD::PM; ++i) {
@@ -281,7 +401,7 @@ __device__ __forceinline__ int regress_from_moments(const RD &rd, const double *
             MTM_UNROLL
             for (int b = a; b < RD::QM; ++b) {
                 if (b < q) {
-                    // SSR = Syy - B'Sxy - E'B
+                    // sum (r - rbar)(r - rbar)' = C_bb - B'C_ab - E'B
                     double s = full[p + a][p + b];
                     MTM_UNROLL
                     for (int i = 0; i < RD::PM; ++i)
@@ -289,7 +409,7 @@ __device__ __forceinline__ int regress_from_moments(const RD &rd, const double *
                     MTM_UNROLL
                     for (int i = 0; i < RD::PM; ++i)
                         if (i < p) s -= E[i][a] * B[i][b];
-                    const double v = (cnt > 1.0) ? (s - cnt * rbar[a] * rbar[b]) / (cnt - 1.0) : qnan();
+                    const double v = (cnt > 1.0) ? s / (cnt - 1.0) : qnan();
                     C_out[a * q + b] = v;
                     C_out[b * q + a] = v;
                 }
@@ -385,16 +505,16 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
             // initial state: mean and np.cov(ddof=1) of the finite z_1 rows
             const double *b1 = st + 1;
             const double n0 = b1[0];
-            double m[MX];
+            double m[MX];  // mean of the centred values; the pivot goes back on for the parameter
             for (int i = 0; i < d; ++i) {
                 m[i] = b1[1 + i] / n0;  // 0/0 = NaN for an empty sample, like np.mean
-                pr[1 + i] = m[i];
+                pr[1 + i] = a0.pivot[i] + m[i];
             }
             int o = 1 + d;
             double *S = pr + 1 + d;
             for (int i = 0; i < d; ++i)
                 for (int j = i; j < d; ++j) {
-                    const double v = (n0 > 1.0) ? (b1[o] - n0 * m[i] * m[j]) / (n0 - 1.0) : qnan();
+                    const double v = (n0 > 1.0) ? fma(-n0 * m[i], m[j], b1[o]) / (n0 - 1.0) : qnan();
                     S[i * d + j] = v;
                     S[j * d + i] = v;
                     ++o;
@@ -402,11 +522,11 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
         } else if (part == 1) {
             double *A = pr + 1 + d + d * d, *G = A + d * d;
             const RegDims<D_, D_> rd{d, d};
-            status |= regress_from_moments(rd, st + 1 + F1, a.alpha, A, G);
+            status |= regress_from_moments(rd, st + 1 + F1, a.alpha, a0.pivot, a0.pivot, A, G);
         } else {
             double *H = pr + 1 + d + 3 * d * d, *Lam = H + d * l;
             const RegDims<D_, L_> rd{d, l};
-            status |= regress_from_moments(rd, st + 1 + F1 + F2, a.alpha, H, Lam);
+            status |= regress_from_moments(rd, st + 1 + F1 + F2, a.alpha, a0.pivot, a0.pivot + MX, H, Lam);
         }
         if (status) atomicOr(&s_status, status);
     }
@@ -422,6 +542,68 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
             ctrl->exit_code = MTM_EXIT_EXHAUSTED;
         }
     }
+}
+
+// ---- pivot: per-feature sum and count of the finite entries of a (T, n, w) array -------------------------------
+// Fixed-order reductions (warp shuffles, then warps, then blocks): the same bits every run.
+__global__ void __launch_bounds__(256) pivot_partial_kernel(const double *__restrict__ a, int64_t n, int64_t ld, int T,
+                                                            int w, double *partials) {
+    double s[MX], c[MX];
+    MTM_UNROLL
+    for (int j = 0; j < MX; ++j) s[j] = c[j] = 0.0;
+    const int64_t rows = (int64_t)T * n;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = r / n, i = r - t * n;
+        const double *row = a + (t * ld + i) * w;
+        MTM_UNROLL
+        for (int j = 0; j < MX; ++j) {
+            if (j < w) {
+                const double y = __ldg(row + j);
+                const bool f = finite_bits(y);
+                s[j] += f ? y : 0.0;
+                c[j] += f ? 1.0 : 0.0;
+            }
+        }
+    }
+    __shared__ double sh[8][2 * MX];
+    MTM_UNROLL
+    for (int j = 0; j < MX; ++j) {
+        for (int o = 16; o > 0; o >>= 1) {
+            s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+            c[j] += __shfl_xor_sync(0xffffffffu, c[j], o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            sh[threadIdx.x >> 5][j] = s[j];
+            sh[threadIdx.x >> 5][MX + j] = c[j];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * MX) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+        partials[(size_t)blockIdx.x * 2 * MX + threadIdx.x] = t;
+    }
+}
+
+__global__ void pivot_reduce_kernel(const double *__restrict__ partials, int grid, double *out16) {
+    if (threadIdx.x < 2 * MX) {
+        double t = 0.0;
+        for (int b = 0; b < grid; ++b) t += partials[(size_t)b * 2 * MX + threadIdx.x];
+        out16[threadIdx.x] = t;
+    }
+}
+
+size_t pivot_scratch_doubles(int sm_count) { return (size_t)sm_count * 8 * 2 * MX; }
+
+cudaError_t launch_pivot_sums(const double *a, int64_t n, int64_t ld, int T, int w, int sm_count, double *scratch,
+                              double *out16, cudaStream_t s) {
+    const int64_t rows = (int64_t)T * n;
+    int grid = (int)((rows + 255) / 256);
+    if (grid > sm_count * 8) grid = sm_count * 8;
+    if (grid < 1) grid = 1;
+    pivot_partial_kernel<<<grid, 256, 0, s>>>(a, n, ld, T, w, scratch);
+    pivot_reduce_kernel<<<1, 32, 0, s>>>(scratch, grid, out16);
+    return cudaGetLastError();
 }
 
 __global__ void counts_kernel(const int32_t *__restrict__ assign, int64_t n, int n_c, unsigned long long *counts) {

@@ -97,7 +97,6 @@ __device__ __forceinline__ void reduce_by_cluster(const double *feat, int F, dou
 struct StatsSmem {
     double *acc;   // n_c * sstride * 2 (hi, lo)
     double *feat;  // FMAX * (kSThreads + 1)
-    int *list;     // kSThreads (unused since the features are staged in sorted order; keeps the layout)
     int *start;    // n_c + 1
     int *wcnt;     // warps * n_c
     __device__ __forceinline__ void carve(unsigned char *base, int n_c, int d, int l) {
@@ -105,8 +104,7 @@ struct StatsSmem {
         const int FMAX = F2 > F3 ? F2 : F3;
         acc = reinterpret_cast<double *>(base);
         feat = acc + 2 * (size_t)n_c * stats_stride(d, l);
-        list = reinterpret_cast<int *>(feat + (size_t)FMAX * (kSThreads + 1));
-        start = list + kSThreads;
+        start = reinterpret_cast<int *>(feat + (size_t)FMAX * (kSThreads + 1));
         wcnt = start + (n_c + 1);
     }
 };
@@ -114,15 +112,27 @@ struct StatsSmem {
 __host__ __device__ inline size_t stats_smem_bytes(int n_c, int d, int l) {
     const int F2 = 1 + 2 * d + d * (2 * d + 1), F3 = 1 + (d + l) + (d + l) * (d + l + 1) / 2;
     const int FMAX = F2 > F3 ? F2 : F3;
-    return (size_t)2 * n_c * stats_stride(d, l) * 8 + (size_t)FMAX * (kSThreads + 1) * 8 + kSThreads * 4 +
+    return (size_t)2 * n_c * stats_stride(d, l) * 8 + (size_t)FMAX * (kSThreads + 1) * 8 +
            (size_t)(n_c + 1) * 4 + (size_t)(kSThreads / 32) * n_c * 4 + 16;
+}
+
+// z_t - pivot: the moments are accumulated about a common point near the data's mean (the per-feature mean of
+// the finite entries, api.cu ensure_pivot), which removes the cancellation of one-pass raw moments when
+// |mean| >> spread; finalize_kernel works with the centred moments directly.  NaN / inf stay non-finite.
+template <int NM>
+__device__ __forceinline__ void centre_row(double (&v)[NM], int n, const double *piv) {
+    MTM_UNROLL
+    for (int k = 0; k < NM; ++k)
+        if (k < n) v[k] -= piv[k];
 }
 
 // One tile.  Every thread of the block must call it (it synchronises); `label` is the cluster of
 // trajectory i (any value outside [0, n_c) = not counted), `i` a valid (clamped) trajectory index.
+// piv: [z pivot (at 0) | x pivot (at MTM_MAX_DIM)], kernel-parameter space (uniform loads).
 template <class DM>
 __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restrict__ z, const double *__restrict__ x,
-                                           int64_t ld, int T, int64_t i, int label, int n_c, unsigned char *smem_base) {
+                                           int64_t ld, int T, int64_t i, int label, int n_c, unsigned char *smem_base,
+                                           const double *piv) {
     // carved here, per call, from ONE base pointer: keeping five derived pointers alive across the caller's
     // E-step loop costs uniform registers that the parameter operands of that loop need
     StatsSmem sm;
@@ -185,10 +195,12 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
         for (int k = 0; k < F2M; ++k) f2[k] = 0.0;
         double zc[DMX], zn[DMX];
         load_row<DMX>(z_i, zc, d, DM::kStatic);
+        centre_row<DMX>(zc, d, piv);
         bool okc = all_finite<DMX>(zc, d);
         add_moments<K1>(f1, zc, d, okc && label >= 0);
         for (int t = 0; t + 1 < T; ++t) {
             load_row<DMX>(z_i + (int64_t)(t + 1) * zs, zn, d, DM::kStatic);
+            centre_row<DMX>(zn, d, piv);
             const bool okn = all_finite<DMX>(zn, d);
             double u[K2];
             MTM_UNROLL
@@ -214,6 +226,8 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
             double zc[DMX], xc[LMX];
             load_row<DMX>(z_i + (int64_t)t * zs, zc, d, DM::kStatic);
             load_row<LMX>(x_i + (int64_t)t * xs, xc, l, DM::kStatic);
+            centre_row<DMX>(zc, d, piv);
+            centre_row<LMX>(xc, l, piv + MTM_MAX_DIM);
             const bool ok = all_finite<DMX>(zc, d) && all_finite<LMX>(xc, l);
             double w[K3];
             MTM_UNROLL

@@ -415,6 +415,14 @@ class MMLinGaussSS_marginalizable:
         presented to the M-step kernels as (z_t, x_t) pairs of a single cluster."""
         X = np.atleast_2d(np.asarray(input_exogenous, dtype=np.float64))
         Y = np.atleast_2d(np.asarray(output_endogenous, dtype=np.float64))
+        if not (np.isfinite(X).all() and np.isfinite(Y).all()):
+            # the moment kernels skip incomplete rows (M_step semantics); the reference's regress gets the rows as
+            # they are and fails on them: numba's lstsq (MMM:1194) / sklearn's input validation (MMM:1226-1227)
+            if alpha > 2 * np_eps:
+                raise ValueError("Input X contains NaN.")
+            raise np.linalg.LinAlgError("Array must not contain infs or NaNs.")
+        if X.shape[1] > C.MTM_MAX_DIM or Y.shape[1] > C.MTM_MAX_DIM:
+            raise C.MtmError(f"regress: at most {C.MTM_MAX_DIM} regressors / responses on the device path")
         eng = Engine.get()
         data = DeviceData(X[None], Y[None], eng.device)
         assign = torch.zeros(X.shape[0], dtype=torch.int32, device=eng.device)

@@ -48,3 +48,8 @@ def g_ext():
 @pytest.fixture(scope="session")
 def g_adni():
     return load_golden("adni_fold0.npz")
+
+
+@pytest.fixture(scope="session")
+def g_cond():
+    return load_golden("conditioning.npz")

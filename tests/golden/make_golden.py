@@ -481,8 +481,73 @@ def golden_extended(ssm):
     print("extended.npz written; scores", out["rand_score"], out["km_score"], out["clf_score"])
 
 
+# ---------------------------------------------------------------------------
+# 7. conditioning: data far from the origin, rank-deficient regression designs
+# ---------------------------------------------------------------------------
+
+
+def golden_conditioning(ssm, mmm):
+    """(a) "offset": a config-2-shaped fit on data moved far from the origin (z + 1e4, x - 3e3): one-pass raw
+    moments would lose ~8 digits here; the reference works on the rows (lstsq, np.cov) and does not.
+    (b) "dupcol": M_step on data whose third state coordinate duplicates the first: both regressions
+    (MMM:1272-1308) have a rank-deficient design and np.linalg.lstsq(rcond=-1) (MMM:1194) returns the
+    minimum-norm solution.  Only the M-step is stored: the fitted covariances are singular by construction,
+    a following E-step is not meaningful.
+    (c) static regress (MMM:1167-1200) on a duplicated-column design and on an underdetermined one."""
+    out = {}
+    rng = np.random.default_rng(20260)
+    n, T, d, l, n_c = 1200, 8, 4, 4, 4
+    z, x, lab, comps = sample_mixture(ssm, rng, n, T, d, l, n_c, 0.2, 0.3)
+    z, x = z + 1.0e4, x - 3.0e3
+    for seed in range(42, 92):
+        try:
+            mdl, tr = traced_train(mmm, n_c, z, x, seed, "random", 0.0, 1000)
+        except BaseException as err:  # noqa: BLE001
+            print("offset seed", seed, "raised", type(err).__name__)
+            continue
+        sizes = [np.bincount(a, minlength=n_c).min() for a in [tr["assign0"]] + tr["assign"]]
+        if min(sizes) >= 20:
+            break
+    else:
+        raise SystemExit("no healthy offset trace")
+    key = "offset"
+    out[f"{key}_z"], out[f"{key}_x"] = z, x
+    out[f"{key}_meta"] = np.array([n, T, d, l, n_c, seed, 1000], dtype=np.int64)
+    out[f"{key}_alpha"] = 0.0
+    store_trace(out, key, mdl, tr)
+    print("offset: seed", seed, "E-steps", len(tr["switches"]), tr["switches"][:8])
+
+    rng = np.random.default_rng(20261)
+    n, T, d, l, n_c = 500, 5, 3, 2, 2
+    z, x, lab, comps = sample_mixture(ssm, rng, n, T, d, l, n_c, 0.15, 0.5)
+    z[:, :, 2] = z[:, :, 0]
+    mdl = mmm.MMLinGaussSS_marginalizable(n_clusters=n_c, states=z, observations=x, random_seed=5, alpha=0.0)
+    mdl.M_step()
+    out["dupcol_z"], out["dupcol_x"] = z, x
+    out["dupcol_assign0"] = np.array(mdl.cluster_assignment)
+    out["dupcol_params"] = pack_model(mdl)
+    print("dupcol: A[0] =", np.round(mdl.transition_matrices[0], 4).tolist())
+
+    rng = np.random.default_rng(20262)
+    X = rng.normal(size=(300, 5))
+    X[:, 3] = X[:, 1]
+    X[:, 4] = 2.0 * X[:, 0] - X[:, 2]
+    Y = X[:, :3] @ rng.normal(size=(3, 4)) + 0.2 * rng.normal(size=(300, 4))
+    B, C = mmm.MMLinGaussSS_marginalizable.regress(X, Y)
+    out["reg_dup_X"], out["reg_dup_Y"], out["reg_dup_B"], out["reg_dup_C"] = X, Y, B, C
+    X2, Y2 = rng.normal(size=(3, 4)), rng.normal(size=(3, 2))
+    B2, C2 = mmm.MMLinGaussSS_marginalizable.regress(X2, Y2)
+    out["reg_under_X"], out["reg_under_Y"], out["reg_under_B"], out["reg_under_C"] = X2, Y2, B2, C2
+    print("regress: rank-deficient |B| =", float(np.abs(B).max()), " underdetermined residual cov =", np.abs(C2).max())
+    np.savez_compressed(os.path.join(HERE, "conditioning.npz"), **out)
+    print("conditioning.npz written")
+
+
 if __name__ == "__main__":
     ssm, mmm, uss = import_reference()
+    if "cond" in sys.argv[1:]:
+        golden_conditioning(ssm, mmm)
+        sys.exit(0)
     if "ext" in (sys.argv[1:] or ["ext"]):
         golden_extended(ssm)
     which = sys.argv[1:] or ["ssm", "em", "restarts", "adni", "lg", "pred"]
