@@ -782,7 +782,7 @@ def test_rank_deficient_regression(g_cond, mix):
     reg = mix.MMLinGaussSS_marginalizable.regress
     B, C = reg(g["reg_under_X"], g["reg_under_Y"])
     assert relerr(B, g["reg_under_B"]) < RTOL
-    assert np.abs(C).max() < 1e-20
+    assert np.abs(C).max() < 1e-12  # exact interpolation: zero up to the rounding of the moment arithmetic
     X, Y = g["reg_dup_X"], g["reg_dup_Y"]
     B, C = reg(X, Y)
     Bmn = np.linalg.pinv(X) @ Y
