@@ -245,11 +245,13 @@ int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64
 
 /* ---- pattern-ordered residency --------------------------------------------------------------------
  * The reference keeps trajectories in the caller's order (MMM:75-81).  For a resident training set the
- * E-step is faster when every aligned group of 32 trajectories shares its per-step "all hidden-state
- * coordinates present" pattern: whenever all of z_t is present the filtered state is a point mass and a
- * warp that agrees on it skips the covariance arithmetic of that step (bit-identical results).
- * mtm_pattern_order: perm_dev (n) int64 out — a stable sort of the trajectories by that pattern (bit t of
- *   the key, t < min(T, 8): all d coordinates of z[t, i, :] finite); perm[p] = index, in the caller's
+ * E-step is faster when every aligned group of 32 trajectories shares its per-step pattern of missing
+ * hidden-state coordinates: when all of z_t is present the filtered state is a point mass, when exactly one
+ * coordinate is missing its covariance has rank one, and a warp that agrees on either skips the generic
+ * covariance arithmetic of that step (bit-identical results).
+ * mtm_pattern_order: perm_dev (n) int64 out — a stable sort of the trajectories by the key
+ *   sum over t < min(T, 8) of s_t 3^(min(T,8)-1-t),  s_t = 2 if all d coordinates of z[t, i, :] are finite,
+ *   1 if exactly one is missing, 0 otherwise (step 0 most significant);  perm[p] = index, in the caller's
  *   order, of the trajectory to store at resident position p.  A pure function of the data.  Synchronises.
  * mtm_permute_f64 / _i32: apply it to a (rows, n, w) array (w = 1 for _i32):
  *   inverse == 0:  dst[r, p, :] = src[r, perm[p], :]   (caller's order -> resident order)

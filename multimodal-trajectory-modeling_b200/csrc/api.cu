@@ -1105,7 +1105,7 @@ int mtm_pattern_order(mtm_handle *h, const mtm_data *data, int64_t *perm_dev) {
     } free_scratch{scratch};
     MTM_CUDA(h, launch_pattern_order(data->z_dev, data->n, data->ld > 0 ? data->ld : data->n, data->T, data->d,
                                      h->sm_count, scratch, perm_dev, h->stream));
-    h->launches += 3;
+    h->launches += (data->T > 4) ? 7 : 4;
     MTM_CUDA(h, cudaStreamSynchronize(h->stream));  // the scratch is freed on return
     return 0;
 }

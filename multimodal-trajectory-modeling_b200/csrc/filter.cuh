@@ -427,6 +427,136 @@ __device__ __forceinline__ void filter_condition_x_point(const DM &dm, FilterSta
     }
 }
 
+// ---- rank-one shortcuts --------------------------------------------------------------------------------------
+// When at most ONE hidden-state coordinate of a step is missing (coordinate j, different from lane to lane),
+// conditioning on the present ones leaves P = sigma2 e_j e_j' with exact zeros everywhere else (and mu_i = z_i for
+// i != j).  The generic code would then push zeros through C = P H, the gains, A'PA; these two functions do only
+// the arithmetic on the one live direction, in the generic code's operation order, so every number has the same
+// bits: row j of H / A is picked with the 0/1 indicator as a multiplicand (exact: one term, the others are zeros),
+// C[j][b] = sigma2 H[j][b], Sx = Lambda + h_j c', P' = Gamma + a_j (sigma2 a_j)'.  `miss` = bit mask of the
+// missing coordinate (0 or one bit set per lane).  Taken on a warp-uniform vote like the point-mass shortcut; at
+// 20 % element-wise missingness 41 % of the steps have exactly one missing coordinate (41 % none).
+
+template <class DM>
+__device__ __forceinline__ double miss_ind(uint32_t miss, int i) {
+    // 1.0 if coordinate i is the missing one else 0.0 (built on the integer pipe)
+    return __hiloint2double(((miss >> i) & 1u) ? 0x3ff00000 : 0, 0);
+}
+
+// (mu, P) <- (mu A, Gamma + A' P A) for P = sigma2 e_j e_j'
+template <class DM, class PV>
+__device__ __forceinline__ void filter_propagate_r1(const DM &dm, FilterState<DM> &f, const PV &p, uint32_t miss) {
+    const int d = dm.d();
+    double nmu[DM::DM], aj[DM::DM];
+    MTM_UNROLL
+    for (int j = 0; j < DM::DM; ++j) nmu[j] = aj[j] = 0.0;
+    double s2 = 0.0;
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            const double mi = f.mu[i];
+            const double ei = miss_ind<DM>(miss, i);
+            s2 += f.P[i][i];
+            MTM_UNROLL
+            for (int j = 0; j < DM::DM; ++j) {
+                if (j < d) {
+                    nmu[j] = fma(mi, p.A(i * d + j), nmu[j]);
+                    aj[j] = fma(ei, p.A(i * d + j), aj[j]);
+                }
+            }
+        }
+    }
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            f.mu[i] = nmu[i];
+            const double ai = aj[i];
+            MTM_UNROLL
+            for (int j = i; j < DM::DM; ++j)
+                if (j < d) f.P[i][j] = fma(ai, s2 * aj[j], p.G(i * d + j));
+        }
+    }
+}
+
+// predictive of x_t and conditioning on its present coordinates for P = sigma2 e_j e_j'
+template <class DM, class PV>
+__device__ __forceinline__ void filter_condition_x_r1(const DM &dm, FilterState<DM> &f, const PV &p,
+                                                      const double (&xt)[DM::LM], uint32_t finmask, uint32_t miss,
+                                                      const bool LAST) {
+    const int d = dm.d(), l = dm.l();
+    double mux[DM::LM], c[DM::LM], hj[DM::LM];
+    double Sx[DM::LM][DM::LM];
+    MTM_UNROLL
+    for (int b = 0; b < DM::LM; ++b) mux[b] = c[b] = hj[b] = 0.0;
+    double muj = 0.0, s2 = 0.0;  // mean and variance of the one uncertain coordinate
+    MTM_UNROLL
+    for (int i = 0; i < DM::DM; ++i) {
+        if (i < d) {
+            const double mi = f.mu[i], pii = f.P[i][i];
+            const double ei = miss_ind<DM>(miss, i);
+            muj = fma(ei, mi, muj);
+            s2 += pii;
+            MTM_UNROLL
+            for (int b = 0; b < DM::LM; ++b) {
+                if (b < l) {
+                    mux[b] = fma(mi, p.H(i * l + b), mux[b]);
+                    c[b] = fma(pii, p.H(i * l + b), c[b]);
+                    hj[b] = fma(ei, p.H(i * l + b), hj[b]);
+                }
+            }
+        }
+    }
+    MTM_UNROLL
+    for (int a = 0; a < DM::LM; ++a) {
+        if (a < l) {
+            MTM_UNROLL
+            for (int b = a; b < DM::LM; ++b)
+                if (b < l) Sx[a][b] = fma(hj[a], c[b], p.Lam(a * l + b));
+        }
+    }
+    MTM_UNROLL
+    for (int j = 0; j < DM::LM; ++j) {
+        if (j < l) {
+            const double y = xt[j];
+            const bool obs = finite_bits(y) && ((finmask >> j) & 1u);
+            const double s = Sx[j][j];
+            const double r = obs ? fast_rcp(s) : 0.0;
+            const double v = obs ? (y - mux[j]) : 0.0;
+            f.q = fma(v * v, r, f.q);
+            if (obs) f.mant *= s;  // predicated DMUL (see filter_condition_z)
+            f.k += obs ? 1 : 0;
+            const double g = c[j] * r;
+            if (!LAST) {
+                muj = fma(g, v, muj);
+                s2 = fma(-g, c[j], s2);
+            }
+            MTM_UNROLL
+            for (int b = j + 1; b < DM::LM; ++b)
+                if (b < l) c[b] = fma(-g, Sx[j][b], c[b]);
+            MTM_UNROLL
+            for (int a = j + 1; a < DM::LM; ++a) {
+                if (a < l) {
+                    const double gx = Sx[j][a] * r;
+                    mux[a] = fma(gx, v, mux[a]);
+                    MTM_UNROLL
+                    for (int b = a; b < DM::LM; ++b)
+                        if (b < l) Sx[a][b] = fma(-gx, Sx[j][b], Sx[a][b]);
+                }
+            }
+        }
+    }
+    if (!LAST) {
+        MTM_UNROLL
+        for (int i = 0; i < DM::DM; ++i) {
+            if (i < d) {
+                const bool mine = (miss >> i) & 1u;
+                f.mu[i] = mine ? muj : f.mu[i];
+                f.P[i][i] = mine ? s2 : f.P[i][i];  // the present coordinates keep their exact zero
+            }
+        }
+    }
+}
+
 // keep the running determinant in range: move the binary exponent of `mant` into `expo`
 template <class DM>
 __device__ __forceinline__ void filter_rescale(FilterState<DM> &f) {
@@ -506,6 +636,8 @@ __device__ __forceinline__ double filter_eval(const DM &dm, const double *__rest
     if (XPRE) load_row<DM::LM>(x_i, xt, dm.l(), DM::kStatic);
     const ParamView<DM, PS> p(dm, psrc);
     bool p_point = false;  // warp-uniform: the posterior of the previous step is a point mass (P == 0, mu == z)
+    bool p_r1 = false;     // warp-uniform: ... has at most one uncertain coordinate per lane (rank-one shortcuts)
+    uint32_t p_miss = 0;   // per lane: bit mask of the coordinates of the previous z_t that were missing
     for (int t = 0; t < T0; ++t) {
         const bool last = (t + 1 == T0);  // warp-uniform
         const int tn = last ? t : t + 1;
@@ -514,22 +646,31 @@ __device__ __forceinline__ double filter_eval(const DM &dm, const double *__rest
         if (XPRE) load_row<DM::LM>(x_i + (int64_t)tn * xs, xn, dm.l(), DM::kStatic);
         else load_row<DM::LM>(x_i + (int64_t)t * xs, xt, dm.l(), DM::kStatic);
         const uint32_t fm = fin[t];
-        // warp-uniform: are all hidden-state coordinates of this step present for all 32 trajectories?
-        bool z_point = false;
+        // warp-uniform votes: are all hidden-state coordinates of this step present for all 32 trajectories
+        // (point mass), or all but at most one per trajectory (rank one)?
+        bool z_point = false, z_r1 = false;
+        uint32_t zmiss = 0;
         if (HAS_Z || tshift != 0) {
-            uint32_t z_all = 1u;
             MTM_UNROLL
             for (int j = 0; j < DM::DM; ++j)
-                if (j < dm.d()) z_all &= (finite_bits(zt[j]) ? 1u : 0u) & (fm >> j);
-            z_point = __all_sync(0xffffffffu, z_all != 0u);
+                if (j < dm.d()) zmiss |= ((finite_bits(zt[j]) ? 1u : 0u) & (fm >> j) & 1u) ? 0u : (1u << j);
+z_point = __all_sync(0xffffffffu, zmiss == 0u);
+            // (both votes unconditional: a short-circuited second vote made ptxas 12.9 drop the uniform-datapath
+            // parameter operands of the whole time loop; the rank-one code exists in the joint kernel only — the
+            // observation-only instantiation keeps its z code as the never-taken shape donor it was before)
+            if (HAS_Z) z_r1 = __all_sync(0xffffffffu, (zmiss & (zmiss - 1u)) == 0u);  // includes the point case
         }
         if (t > 0) {
             if (p_point) filter_propagate_point(dm, f, p);
+            else if (HAS_Z && p_r1) filter_propagate_r1(dm, f, p, p_miss);
             else filter_propagate(dm, f, p);
         }
         if (HAS_Z || tshift != 0) filter_condition_z(dm, f, zt, fm & 0xffffu);
         if (z_point) filter_condition_x_point(dm, f, p, xt, fm >> 16);
+        else if (HAS_Z && z_r1) filter_condition_x_r1(dm, f, p, xt, fm >> 16, zmiss, last);
         else filter_condition_x(dm, f, p, xt, fm >> 16, last);
+        p_r1 = z_r1;
+        p_miss = zmiss;
         p_point = z_point;
         filter_rescale(f);
         if (PREFIX) pre[(int64_t)t * pre_stride] = filter_finish(f, bad);

@@ -520,8 +520,9 @@ def test_many_clusters_vs_oracle(mix, n_c):
 
 
 def test_pattern_order(eng):
-    """mtm_pattern_order / mtm_permute_*: a stable sort by the per-step "z complete" pattern; gathers exact;
-    inverse round trip; the E-step gives the same bits in either order (point-mass shortcut vs generic path)."""
+    """mtm_pattern_order / mtm_permute_*: a stable sort by the per-step "none / one / more hidden-state coordinates
+    missing" pattern; gathers exact; inverse round trip; the E-step gives the same bits in either order (point-mass
+    and rank-one shortcuts vs generic path)."""
     import mtm_b200
 
     for (n, T, d, l) in ((70_003, 8, 4, 4), (5_000, 3, 2, 4), (33, 12, 1, 1), (2, 8, 4, 4)):
@@ -532,8 +533,9 @@ def test_pattern_order(eng):
         perm = ordered.perm.cpu().numpy()
         assert np.array_equal(np.sort(perm), np.arange(n))
         key = np.zeros(n, dtype=np.int64)
-        for t in range(min(T, 8)):
-            key |= np.all(np.isfinite(z[t]), axis=1).astype(np.int64) << t
+        for t in range(min(T, 8)):  # base-3 digit per step, step 0 most significant: 2 complete, 1 one missing
+            missing = np.sum(~np.isfinite(z[t]), axis=1)
+            key = key * 3 + np.where(missing == 0, 2, np.where(missing == 1, 1, 0))
         assert np.array_equal(perm, np.argsort(key, kind="stable"))
         assert np.array_equal(ordered.z.cpu().numpy(), z[:, perm], equal_nan=True)
         assert np.array_equal(ordered.x.cpu().numpy(), x[:, perm], equal_nan=True)
