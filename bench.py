@@ -397,6 +397,21 @@ def data_stats(torch, z, x):
     return out
 
 
+def warp_step_classes(torch, z_resident):
+    """Fractions of the (warp, time step) pairs of the resident order that take each code path of the E-step:
+    point mass (no hidden-state coordinate missing in any of the 32 trajectories), rank one (at most one per
+    trajectory), generic."""
+    T, n, _ = z_resident.shape
+    miss = (~torch.isfinite(z_resident)).sum(dim=2)                      # (T, n)
+    pad = (-n) % 32
+    if pad:
+        miss = torch.cat([miss, miss[:, -1:].expand(T, pad)], dim=1)
+    worst = miss.reshape(T, -1, 32).amax(dim=2)                          # (T, warps)
+    tot = float(worst.numel())
+    return {"point": float((worst == 0).sum().item()) / tot, "rank_one": float((worst == 1).sum().item()) / tot,
+            "generic": float((worst >= 2).sum().item()) / tot}
+
+
 def oracle_gate(ctx, z, x, params, n_c, T, npre=4096, d=None):
     """E-step of a caller-order prefix against the sequential C oracle (ll, assignments, closest call)."""
     from oracle import cport as oc
@@ -544,6 +559,7 @@ def leg_em(ctx, cfg, steps, warmup, tag, pattern_order=True):
     a0 = labels_global(n_total, lo, hi, n_c, ctx.device)
     ds = data_stats(torch, z, x)
     run = EmRunner(ctx, z, x, a0, n_c, pattern_order=pattern_order)
+    wsc = warp_step_classes(torch, run.data.z)
     run.m_step()  # parameters of the initial assignment (train()'s first M-step)
     for _ in range(warmup):
         run.phase(3)
@@ -563,7 +579,7 @@ def leg_em(ctx, cfg, steps, warmup, tag, pattern_order=True):
     out = {"tag": tag, "n_total": n_total, "n_per_gpu": n_loc, "n_c": n_c, "steps": steps, "ms_per_step": ms_step,
            "value": n_total * n_c / (ms_step * 1e-3), "em_iters_per_s": 1e3 / ms_step, "clocks": clk.summary(),
            "gpu_launches": int(launches), "workload_check": chk, "order_ms": run.order_ms,
-           "present_scalars_per_trajectory": {"z": ds["kz"], "x": ds["kx"]},
+           "present_scalars_per_trajectory": {"z": ds["kz"], "x": ds["kx"]}, "warp_step_paths": wsc,
            "roofline": em_roofline(ctx, cfg, ds, n_loc, ms_e, ms_m, pattern_order,
                                    "estep_kernel<4,4,HAS_Z=1,CONSTP=1> with the M-step statistics fused in (the "
                                    "timed span also holds the two ~10 us reduction kernels and, for N > 1, the "
@@ -878,7 +894,17 @@ def main():
         b = run_cpu_arm(args, cfg, steps=1, warmup=0)
         cpu_base = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    class_gate = None
     if world > 1:
+        # the drop-in class sharding itself over the same process group (its own handle and communicator)
+        from mtm_b200.framework import marginalizable_mixture_model as mixmodel
+        from tools.class_dist_checks import class_checks
+
+        failures = class_checks(mixmodel, world, rank)
+        class_gate = {"ok": not failures, "failures": failures[:5],
+                      "what": "MMLinGaussSS_marginalizable built from the full arrays on every rank: golden traces c2s / "
+                              "adnish / guardexit, held-out and observation-only predictions, restart selection, "
+                              "communicator re-attach"}
         ctx.eng.comm_destroy()
     multi = None
     if world > 1 and rank == 0 and not args.no_replay:
@@ -891,6 +917,7 @@ def main():
     if rank == 0:
         parity = main_leg.pop("parity")
         parity["multi_gpu"] = multi
+        parity["class_sharded"] = class_gate
         chk = main_leg["workload_check"]
         line = {"metric": METRIC, "value": main_leg["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": main_leg["ms_per_step"], "higher_is_better": True,
@@ -912,7 +939,7 @@ def main():
                 "roofline": main_leg["roofline"], "cpu_baseline": cpu_base, "parity": parity,
                 "workload_check": chk, "state": main_leg["state"],
                 "present_scalars_per_trajectory": main_leg["present_scalars_per_trajectory"],
-                "configs": configs}
+                "warp_step_paths": main_leg["warp_step_paths"], "configs": configs}
         bad = []
         if not chk["ok"]:
             bad.append(f"timed EM iteration is degenerate: {chk}")
@@ -920,6 +947,8 @@ def main():
             bad.append("oracle parity gate failed")
         if multi is not None and not (multi["assignments_equal"] and multi["params_max_rel_err"] < 1e-9):
             bad.append("N-GPU fit differs from the single-GPU fit")
+        if class_gate is not None and not class_gate["ok"]:
+            bad.append("sharded drop-in class differs from the reference's golden traces")
         if bad:
             line["invalid"] = bad
             rc = 1

@@ -142,11 +142,15 @@ __device__ __forceinline__ bool chol_factor(const RD &rd, double (&M)[RD::PM][RD
     MTM_UNROLL
     for (int j = 0; j < RD::PM; ++j) {
         if (j < p) {
-            double s = M[j][j] + alpha;
+            const double djj = M[j][j] + alpha;
+            double s = djj;
             MTM_UNROLL
             for (int k = 0; k < RD::PM; ++k)
                 if (k < j) s -= M[j][k] * M[j][k];
-            ok = ok && (s > 0.0);
+            // least squares: a pivot below ~64 eps of its diagonal entry is rounding noise of a rank-deficient
+            // scatter matrix (exactly dependent columns leave +-1e-17 here), not information: hand over to the
+            // minimum-norm solve.  Ridge: alpha keeps every pivot well above that; only non-finite input fails.
+            ok = ok && (alpha > 0.0 ? s > 0.0 : s > 1.5e-14 * djj);
             const double dj = sqrt(s);
             M[j][j] = dj;
             const double inv = 1.0 / dj;

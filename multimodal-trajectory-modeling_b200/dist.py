@@ -45,6 +45,42 @@ def attach(engine, group=None) -> None:
         engine.p2p_attach(handles, world, rank)
 
 
+def active_group(group=None):
+    """(world, rank) of the process group a model should shard over, or (1, 0): no initialised
+    torch.distributed group, a single-rank group, or group=False (explicitly local)."""
+    if group is False or not (tdist.is_available() and tdist.is_initialized()):
+        return 1, 0
+    return tdist.get_world_size(group), tdist.get_rank(group)
+
+
+def _on_wire(t, group):
+    """gloo moves host tensors, nccl device tensors."""
+    return t.cpu() if tdist.get_backend(group) == "gloo" else t
+
+
+def gather_last(t, n_full: int, world: int, rank: int, group=None):
+    """All-gather the ragged shards of the LAST axis: t is (..., n_rank) on every rank, the result (..., n_full)
+    on every rank (same device as t).  Shard r covers shard_bounds(n_full, world, r)."""
+    if world == 1:
+        return t
+    sizes = [shard_bounds(n_full, world, r)[1] - shard_bounds(n_full, world, r)[0] for r in range(world)]
+    assert int(t.shape[-1]) == sizes[rank], (tuple(t.shape), sizes, rank)
+    pad = max(sizes)
+    buf = t.new_zeros(tuple(t.shape[:-1]) + (pad,))
+    buf[..., : sizes[rank]] = t
+    buf = _on_wire(buf.contiguous(), group)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    tdist.all_gather(out, buf, group=group)
+    return torch.cat([o[..., :s] for o, s in zip(out, sizes)], dim=-1).to(t.device)
+
+
+def sum_int(value: int, device, group=None) -> int:
+    """Sum of a host integer over the ranks (switch counts of a sharded E_step)."""
+    t = _on_wire(torch.tensor([int(value)], dtype=torch.int64, device=device), group)
+    tdist.all_reduce(t, group=group)
+    return int(t.item())
+
+
 def detach(engine) -> None:
     if engine.world > 1:
         engine.comm_destroy()

@@ -104,6 +104,22 @@ class DeviceData:
 
 class Engine:
     _cache: dict = {}
+    _sharded: dict = {}
+
+    @classmethod
+    def get_sharded(cls, device=None, group=None) -> "Engine":
+        """The engine of `device` whose handle carries the communicator of `group` (created and attached once,
+        collectively on all ranks of the group).  Kept apart from Engine.get(): that one never all-reduces, so
+        rank-local work (a static regress, held-out data every rank holds in full) stays rank-local."""
+        from . import dist as mdist
+
+        base = cls.get(device)
+        key = (base.device.index, id(group))
+        if key not in cls._sharded:
+            eng = Engine(base.device)
+            mdist.attach(eng, group)
+            cls._sharded[key] = eng
+        return cls._sharded[key]
 
     @classmethod
     def get(cls, device=None) -> "Engine":

@@ -24,6 +24,7 @@ import torch
 
 try:
     from .. import _capi as C
+    from .. import dist as mdist
     from ..engine import DeviceData, Engine
 except ImportError:
     # Imported as the TOP-LEVEL package `framework` (the package directory was put first on sys.path so that
@@ -36,6 +37,7 @@ except ImportError:
         _sys.path.insert(0, _root)
     import mtm_b200 as _pkg  # noqa: F401
     from mtm_b200 import _capi as C
+    from mtm_b200 import dist as mdist
     from mtm_b200.engine import DeviceData, Engine
 
 np_eps = np.finfo(float).eps
@@ -74,10 +76,20 @@ class MMLinGaussSS_marginalizable:
         alpha: float = 0.0,
         *,
         device=None,
+        group=None,
         _shared_data: DeviceData = None,
     ):
         """Same arguments as the reference constructor (MMM:45-53); ``device`` (keyword-only,
-        optional) picks the CUDA device."""
+        optional) picks the CUDA device.
+
+        Multi-GPU: when a ``torch.distributed`` process group is initialised (one process per GPU, e.g. under
+        torchrun) every rank constructs the model with the SAME full arrays, exactly like the single-process
+        script, and the class shards the trajectory axis itself: a rank keeps rows
+        ``dist.shard_bounds(n, world, rank)`` on its GPU, every fit / score is one collective call with one
+        all-reduce of the sufficient statistics per EM iteration, and labels / (n_c, n) matrices are all-gathered,
+        so that every rank ends with the reference's full ``cluster_assignment`` and identical parameters.
+        ``group``: the process group to shard over (default: the world group); ``group=False`` keeps the model
+        local to this process."""
         states, observations = map(np.atleast_3d, (states, observations))
         self.n_clusters = int(n_clusters)
         self.states = np.array(states)
@@ -110,6 +122,12 @@ class MMLinGaussSS_marginalizable:
                            .astimezone().isoformat())
         self.last_trained = None
 
+        self._group = group
+        self._world, self._rank = mdist.active_group(group)
+        if self._world > 1 and self.n_data < 32 * self._world:
+            self._world, self._rank = 1, 0  # too small to shard: every rank fits its own full copy
+        if self._world > 1 and device is None and "LOCAL_RANK" in os.environ:
+            device = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
         self._device = device
         self._data = _shared_data  # uploaded lazily
         self.fit_info = None       # dict from the last train(): exit, n_e_steps, switches, ...
@@ -175,13 +193,43 @@ class MMLinGaussSS_marginalizable:
     # ------------------------------------------------------------------ device plumbing
     @property
     def engine(self) -> Engine:
+        """The engine of the training set: with the group's communicator when the model is sharded."""
+        if self._world > 1:
+            return Engine.get_sharded(self._device, self._group if self._group is not False else None)
         return Engine.get(self._device)
+
+    def _engine_for(self, data) -> Engine:
+        return self.engine if getattr(data, "shard", None) else Engine.get(self._device)
+
+    def _shard_of(self, n):
+        """(lo, hi) of this rank for an n-trajectory set, or None if the set is not sharded."""
+        if self._world == 1 or n < 32 * self._world:
+            return None
+        return mdist.shard_bounds(n, self._world, self._rank)
+
+    def _make_data(self, states, observations, pattern_order=False) -> DeviceData:
+        """Device copy of (this rank's rows of) a data set; ``data.shard`` = (n, lo, hi) when sharded."""
+        n = observations.shape[1]
+        sh = self._shard_of(n)
+        if sh is not None:
+            states = None if states is None else np.ascontiguousarray(states[:, sh[0]:sh[1]])
+            observations = np.ascontiguousarray(observations[:, sh[0]:sh[1]])
+        data = DeviceData(states, observations, Engine.get(self._device).device, pattern_order=pattern_order)
+        data.shard = None if sh is None else (n, sh[0], sh[1])
+        return data
+
+    def _gather(self, data, t):
+        """(..., n_rank) device tensor in the caller's order -> (..., n) on every rank."""
+        sh = getattr(data, "shard", None)
+        if sh is None or t is None:
+            return t
+        return mdist.gather_last(t, sh[0], self._world, self._rank, self._group if self._group is not False else None)
 
     def _train_data(self) -> DeviceData:
         if self._data is None:
-            # resident order = grouped by the per-step "z complete" pattern (engine.DeviceData); everything
+            # resident order = grouped by the per-step missing-coordinate pattern (engine.DeviceData); everything
             # that leaves this class is translated back to the caller's order
-            self._data = DeviceData(self.states, self.observations, self.engine.device, pattern_order=True)
+            self._data = self._make_data(self.states, self.observations, pattern_order=True)
         return self._data
 
     def _packed_params(self) -> np.ndarray:
@@ -220,11 +268,16 @@ class MMLinGaussSS_marginalizable:
         self.measurement_covs = take((l, l))
 
     def _assign_dev(self):
-        """Current labels as an int32 device tensor in the training set's resident order."""
-        return self._train_data().to_resident(np.ascontiguousarray(self.cluster_assignment, dtype=np.int32))
+        """Current labels (this rank's rows) as an int32 device tensor in the training set's resident order."""
+        data = self._train_data()
+        lab = self.cluster_assignment
+        if getattr(data, "shard", None):
+            lab = lab[data.shard[1]:data.shard[2]]
+        return data.to_resident(np.ascontiguousarray(lab, dtype=np.int32))
 
     def _assign_host(self, assign_dev) -> np.ndarray:
-        return self._train_data().from_resident(assign_dev).cpu().numpy().astype(np.int64)
+        data = self._train_data()
+        return self._gather(data, data.from_resident(assign_dev)).cpu().numpy().astype(np.int64)
 
     def _resolve(self, states, observations):
         """The reference's data-override rule: if `states` is None BOTH come from the training
@@ -233,16 +286,26 @@ class MMLinGaussSS_marginalizable:
             return self._train_data()
         if observations is None:
             raise TypeError("observations must be given together with states")
-        return DeviceData(states, observations, self.engine.device)
+        return self._make_data(np.atleast_3d(np.asarray(states, dtype=np.float64)),
+                               np.atleast_3d(np.asarray(observations, dtype=np.float64)))
 
     # ------------------------------------------------------------------ likelihoods
     def _estep(self, data, T0, *, ll=False, probs=False, prenorm=False, d=None):
-        res = self.engine.estep(data, self._packed_params(), self.n_clusters, T0, want_ll=ll, want_probs=probs,
-                                want_prenorm=prenorm, d=d)
-        _raise_for_status(res["status"], self.alpha)
-        for k in ("assign", "ll", "probs", "prenorm"):  # resident order -> caller's order
-            res[k] = data.from_resident(res[k])
+        res = self._engine_for(data).estep(data, self._packed_params(), self.n_clusters, T0, want_ll=ll,
+                                           want_probs=probs, want_prenorm=prenorm, d=d)
+        status = res["status"]
+        if getattr(data, "shard", None):  # every rank must raise (or not) together
+            status = self._or_status(status)
+        _raise_for_status(status, self.alpha)
+        for k in ("assign", "ll", "probs", "prenorm"):  # resident order -> caller's order (-> all ranks' rows)
+            res[k] = self._gather(data, data.from_resident(res[k]))
         return res
+
+    def _or_status(self, status: int) -> int:
+        """Union of the ranks' status bits (each bit summed separately)."""
+        grp = self._group if self._group is not False else None
+        dev = Engine.get(self._device).device
+        return sum(b for b in (1, 2, 4, 8, 16) if mdist.sum_int(1 if status & b else 0, dev, grp) > 0)
 
     def conditional_log_likelihoods_first_T0_steps(self, c: int, T0: int, *, states=None, observations=None):
         """log p(z_i, x_i | cluster c) on steps 1..T0 (MMM:439-494)."""
@@ -288,9 +351,12 @@ class MMLinGaussSS_marginalizable:
     def _propensities_over_time(self, data, T0, d):
         """All T0 prefixes from ONE launch (mtm_estep_prefix): the sequential filter passes through every
         prefix likelihood anyway; the reference re-evaluates each prefix from scratch."""
-        L, status = self.engine.estep_prefix(data, self._packed_params(), self.n_clusters, T0, d=d)
+        L, status = self._engine_for(data).estep_prefix(data, self._packed_params(), self.n_clusters, T0, d=d)
+        if getattr(data, "shard", None):
+            status = self._or_status(status)
         _raise_for_status(status, self.alpha)
-        L = data.from_resident(L.reshape(T0 * self.n_clusters, data.n)).reshape(T0, self.n_clusters, data.n)
+        L = self._gather(data, data.from_resident(L.reshape(T0 * self.n_clusters, data.n)))
+        L = L.reshape(T0, self.n_clusters, -1)
         pc_t = self.cluster_propensities[None, None, :] * np.exp(L.cpu().numpy().transpose(0, 2, 1))
         pc_t /= np.sum(pc_t, axis=-1, keepdims=True)
         assert np.all(pc_t >= 0.0) and np.allclose(np.sum(pc_t, axis=-1), 1.0)
@@ -307,8 +373,9 @@ class MMLinGaussSS_marginalizable:
             tr = self._train_data()
             od = DeviceData.__new__(DeviceData)
             od.z, od.x, od.T, od.n, od.l, od.d, od.perm = None, tr.x, tr.T, tr.n, tr.l, None, tr.perm
+            od.shard = getattr(tr, "shard", None)
             return od
-        return DeviceData(None, observations, self.engine.device)
+        return self._make_data(None, np.atleast_3d(np.asarray(observations, dtype=np.float64)))
 
     def observed_condl_log_lik_first_T0_steps(self, c: int, T0: int, *, observations=None):
         """log p(x_i | cluster c) on steps 1..T0 (MMM:997-1048)."""
@@ -333,7 +400,10 @@ class MMLinGaussSS_marginalizable:
     # ---- scores --------------------------------------------------------------------------------
     def _score(self, states, observations):
         data = self._resolve(states, observations)
-        q, ll, status = self.engine.score(data, self._packed_params(), self.n_clusters)
+        # sharded data: the library all-reduces the two sums; data every rank holds in full: the local engine
+        q, ll, status = self._engine_for(data).score(data, self._packed_params(), self.n_clusters)
+        if getattr(data, "shard", None):
+            status = self._or_status(status)
         _raise_for_status(status, self.alpha)
         return q, ll
 
@@ -439,9 +509,13 @@ class MMLinGaussSS_marginalizable:
         assign = self._assign_dev()
         res = eng.estep(self._train_data(), self._packed_params(), self.n_clusters, self.n_timesteps, assign=assign,
                         count_switches=True)
-        _raise_for_status(res["status"], self.alpha)
+        status, n_sw = res["status"], int(res["n_switches"])
+        if self._world > 1:
+            status = self._or_status(status)
+            n_sw = mdist.sum_int(n_sw, eng.device, self._group if self._group is not False else None)
+        _raise_for_status(status, self.alpha)
         self.cluster_assignment = self._assign_host(assign)
-        return int(res["n_switches"])
+        return n_sw
 
     def M_step(self) -> None:
         """Parameters from the current hard assignment (MMM:1254-1308)."""
@@ -497,7 +571,8 @@ class MMLinGaussSS_marginalizable:
         shared = self._train_data()
         best_mdl = MMLinGaussSS_marginalizable(n_clusters=self.n_clusters, states=self.states,
                                                observations=self.observations, random_seed=0, init="kmeans",
-                                               alpha=self.alpha, device=self._device, _shared_data=shared)
+                                               alpha=self.alpha, device=self._device, group=self._group,
+                                               _shared_data=shared)
         try:
             best_mdl = best_mdl.train(verbose=verbose, n_steps=n_steps)
         except Exception:  # noqa: BLE001 - the reference swallows every failure of a start
@@ -520,7 +595,7 @@ class MMLinGaussSS_marginalizable:
                 pass
         if not np.isfinite(best_mdl.e_complete_data_log_lik()):
             raise Exception("training failed")
-        if use_cache:
+        if use_cache and self._rank == 0:  # sharded: every rank holds the same model, one of them writes it
             best_mdl.to_pickle()
         if return_objectives:
             return best_mdl, np.array(objective_list)
@@ -530,19 +605,26 @@ class MMLinGaussSS_marginalizable:
         """[(status, Q, factory)] for seeds 100 .. 100+n_starts-1 (MMM:1449-1455), fitted together."""
         eng = self.engine
         n, k = self.n_data, self.n_clusters
+        lo, hi = (shared.shard[1], shared.shard[2]) if getattr(shared, "shard", None) else (0, n)
         if n >= 200_000:
             # large data: draw rng.integers(0, k, n) for every seed ON the device (bit-identical to numpy,
-            # mtm_random_labels) instead of n_starts host draws + uploads
-            assign = torch.empty((n_starts, n), dtype=torch.int32, device=eng.device)
+            # mtm_random_labels) instead of n_starts host draws + uploads; a sharded model keeps its rows of it
+            assign = torch.empty((n_starts, hi - lo), dtype=torch.int32, device=eng.device)
+            full = torch.empty(n, dtype=torch.int32, device=eng.device) if (lo, hi) != (0, n) else None
             for i in range(n_starts):
-                eng.random_labels(100 + i, k, n, out=assign[i])
+                if full is None:
+                    eng.random_labels(100 + i, k, n, out=assign[i])
+                else:
+                    eng.random_labels(100 + i, k, n, out=full)
+                    assign[i].copy_(full[lo:hi])
         else:
-            a0 = np.stack([np.random.default_rng(seed=100 + i).integers(low=0, high=k, size=n)
+            a0 = np.stack([np.random.default_rng(seed=100 + i).integers(low=0, high=k, size=n)[lo:hi]
                            for i in range(n_starts)]).astype(np.int32)
             assign = torch.from_numpy(a0).to(eng.device)
         assign = shared.to_resident(assign)
         params, infos, scores, sstat = eng.sweep_fit(shared, assign, k, self.alpha, n_steps)
-        params_h, assign_h = params.cpu().numpy(), shared.from_resident(assign).cpu().numpy()
+        params_h = params.cpu().numpy()
+        assign_h = self._gather(shared, shared.from_resident(assign)).cpu().numpy()
         out = []
         for i in range(n_starts):
             info = infos[i]
@@ -550,7 +632,7 @@ class MMLinGaussSS_marginalizable:
             def make(i=i, info=info):
                 mdl = MMLinGaussSS_marginalizable(n_clusters=k, states=self.states, observations=self.observations,
                                                   random_seed=100 + i, alpha=self.alpha, device=self._device,
-                                                  _shared_data=shared)
+                                                  group=self._group, _shared_data=shared)
                 mdl.cluster_assignment = assign_h[i].astype(np.int64)
                 mdl.fit_info = info
                 if info["exit"] != "guard0":

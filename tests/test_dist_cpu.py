@@ -86,18 +86,24 @@ def _worker(rank, world, port, q):
     assert np.array_equal(a_loc, g[f"{key}_assign0"][lo:hi])
     # local statistics -> all-reduce -> identical finalise on every rank
     st = torch.from_numpy(oracle_stats(zs, xs, a_loc, n_c))
-    tail = torch.tensor([0.0, float(hi - lo)], dtype=torch.float64)
+    tail = torch.tensor([0.0, float(hi - lo), 0.0, 0.0], dtype=torch.float64)  # [switches | n | NONFINITE | SINGULAR]
     buf = torch.cat([st.reshape(-1), tail])
     dist.all_reduce(buf)
     stride = mtm_b200._capi.load().mtm_stats_stride(d, l)
     assert st.shape[1] == stride
-    n_total = int(buf[-1].item())
-    P = finalize_from_stats(buf[:-2].reshape(n_c, stride).numpy(), d, l, n_total, 0.0)
+    n_total = int(buf[-3].item())
+    P = finalize_from_stats(buf[:-4].reshape(n_c, stride).numpy(), d, l, n_total, 0.0)
     ref = od.m_step(z, x, g[f"{key}_assign0"], n_c, 0.0).packed()
     err = float(np.max(np.abs(P - ref) / np.maximum(1e-6, np.abs(ref))))
     # gather of ragged label shards
     full = mdist.gather_assignments(torch.from_numpy(a_loc.astype(np.int32)), n, world, rank)
     ok = err < 1e-9 and n_total == n and np.array_equal(full, g[f"{key}_assign0"])
+    # host-side helpers of the sharded drop-in class: ragged all-gather of the last axis, integer sums, group probe
+    part = torch.arange(lo, hi, dtype=torch.float64).repeat(3, 1) * torch.tensor([[1.0], [2.0], [3.0]])
+    whole = mdist.gather_last(part, n, world, rank)
+    ok = ok and tuple(whole.shape) == (3, n) and bool(torch.equal(whole[1], 2.0 * torch.arange(n, dtype=torch.float64)))
+    ok = ok and mdist.sum_int(rank + 1, "cpu") == world * (world + 1) // 2
+    ok = ok and mdist.active_group() == (world, rank) and mdist.active_group(False) == (1, 0)
     # every rank ends with bit-identical parameters
     mine = torch.from_numpy(P.copy())
     other = mine.clone()
