@@ -59,6 +59,8 @@ extern "C" {
 #define MTM_EXIT_GUARD0 4     /* min cluster size <= 3 before the first M-step: nothing ran [MMM:1328-1336] */
 #define MTM_EXIT_ERROR 5      /* a numerical failure on which the reference raises (status != 0): the loop
                                  stops at that step so the host can raise the same exception */
+#define MTM_EXIT_EMPTY 6      /* mtm_em_fit_ext only: an E-step left a cluster without members; the labels of
+                                 that E-step are discarded (framework_extended/state_space_model_mixture.py:122-124) */
 
 typedef struct mtm_handle mtm_handle;
 
@@ -194,6 +196,29 @@ int mtm_em_step_host(mtm_handle *h, const double *z_host, const double *x_host, 
  * [statistics | n_switches] per iteration; all ranks return identical params/info. */
 int mtm_em_fit(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assign_dev,
                double *params_dev, mtm_fit_info *info, int64_t *switches_host, int switches_cap);
+
+/* ---- framework_extended: mixtures / classifiers with linear-Gaussian components -----------------------
+ * The reference's second mixture class (framework_extended/state_space_model_mixture.py, SSMM) fits every
+ * cluster with StateSpaceLinearGaussian.fit (framework_extended/state_space_model_linear_gaussian.py:39-79,
+ * SSLG), whose estimates differ from MMLinGaussSS_marginalizable.M_step in two places:
+ *   - initial-state mean = np.nanmean per coordinate (every non-NaN entry of z_1 counts, SSLG:43-44); the
+ *     covariance still uses the completely finite rows (SSLG:45-47);
+ *   - alpha <= 2 eps: util.regress (util/util_state_space.py:33-61) = normal equations with a fixed 1e-6
+ *     ridge; alpha > 2 eps: util.regress_alpha (Ridge, :64-94), as in the other class.
+ * mtm_mstep_ext: those estimates for all n_c label values in ONE pass over the resident set (the M-step of
+ *   SSMM._M_step, SSMM:134-149; the per-class fits of StateSpaceModelClassifier.fit, classifier :33-44; a
+ *   single component's fit with n_c = 1).  Same arguments as mtm_mstep.
+ * mtm_em_fit_ext: the EM loop of SSMM.fit (SSMM:262-276) resident on the device:
+ *     M -> { E ; stop if a cluster got no member (labels of this E-step discarded) ; stop if 0 switches ;
+ *            stop if min cluster size <= 3 ; M }
+ *   There is no guard before the first M-step (the caller re-draws a near-empty initial assignment, SSMM:251-260).
+ *   assign_prev_dev: (n) int32 scratch: the labels before the last executed E-step, which are the model's
+ *   labels on MTM_EXIT_EMPTY / MTM_EXIT_ERROR (the reference leaves the assignment untouched when its E-step
+ *   raises).  Not sharded: a communicator must not be attached. */
+int mtm_mstep_ext(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, double *params_dev,
+                  mtm_estep_info *info);
+int mtm_em_fit_ext(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assign_dev, int32_t *assign_prev_dev,
+                   double *params_dev, mtm_fit_info *info, int64_t *switches_host, int switches_cap);
 
 /* ---- batched restarts (kernel 4) -------------------------------------------------------------------
  * n_restarts independent EM fits of the resident set with the same n_c, advanced in lock-step: every

@@ -23,8 +23,8 @@ STATUS_EMPTY_FIT = 4
 STATUS_CHOL_FAIL = 8
 STATUS_COMM_TIMEOUT = 16
 
-EXIT_RUNNING, EXIT_CONVERGED, EXIT_GUARD, EXIT_EXHAUSTED, EXIT_GUARD0, EXIT_ERROR = 0, 1, 2, 3, 4, 5
-EXIT_NAMES = {0: "running", 1: "converged", 2: "guard", 3: "exhausted", 4: "guard0", 5: "error"}
+EXIT_RUNNING, EXIT_CONVERGED, EXIT_GUARD, EXIT_EXHAUSTED, EXIT_GUARD0, EXIT_ERROR, EXIT_EMPTY = 0, 1, 2, 3, 4, 5, 6
+EXIT_NAMES = {0: "running", 1: "converged", 2: "guard", 3: "exhausted", 4: "guard0", 5: "error", 6: "empty"}
 
 
 class MtmError(RuntimeError):
@@ -68,6 +68,8 @@ SIGNATURES = {
     "mtm_em_step_host": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _i,
                               ctypes.POINTER(EStepInfo)]),
     "mtm_em_fit": (_i, [_vp, _i, _d, _i, _vp, _vp, ctypes.POINTER(FitInfo), ctypes.POINTER(_i64), _i]),
+    "mtm_mstep_ext": (_i, [_vp, _vp, _i, _d, _vp, ctypes.POINTER(EStepInfo)]),
+    "mtm_em_fit_ext": (_i, [_vp, _i, _d, _i, _vp, _vp, _vp, ctypes.POINTER(FitInfo), ctypes.POINTER(_i64), _i]),
     "mtm_sweep_fit": (_i, [_vp, _i, _i, _d, _i, _vp, _vp, ctypes.POINTER(FitInfo), ctypes.POINTER(_d),
                            ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_i64), _i]),
     "mtm_comm_unique_id": (_i, [_vp]),

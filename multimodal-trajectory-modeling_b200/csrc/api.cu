@@ -107,6 +107,8 @@ struct mtm_handle {
     int pivot_world = 0;
     double *d_pivot = nullptr;  // [32 sums/counts | scratch]
     size_t pivot_cap = 0;
+    double *d_nanmean = nullptr;  // framework_extended: [(n_c, 2d) sums/counts | scratch]
+    size_t nanmean_cap = 0;
     long long *d_rng = nullptr;  // mtm_random_labels: rejection list [kRngCap] + counter, allocated on first use
     long long *h_rng = nullptr;  // pinned mirror
     std::string err;
@@ -363,9 +365,23 @@ int enqueue_e_and_stats(mtm_handle *h, int n_c, const double *params, int32_t *a
     return enqueue_stats(h, assign, n_c, check_done, 1, R);
 }
 
-int enqueue_finalize(mtm_handle *h, int n_c, double alpha, double *params, int mode, int n_steps, int R = 1) {
+// framework_extended: np.nanmean statistics of z_1 under `assign` into h->d_nanmean
+int enqueue_nanmean(mtm_handle *h, const int32_t *assign, int n_c, int check_done) {
+    const mtm_data &dt = h->data;
+    const size_t n_out = (size_t)n_c * 2 * dt.d;
+    if (int rc = ensure(h, h->d_nanmean, h->nanmean_cap, n_out + nanmean_scratch_doubles(n_c, dt.d, h->sm_count))) return rc;
+    MTM_CUDA(h, launch_nanmean(dt.z_dev, dt.n, dt.d, assign, n_c, h->sm_count, h->d_nanmean + n_out, h->d_nanmean,
+                               h->d_ctrl, check_done, h->stream));
+    h->launches += 2;
+    return 0;
+}
+
+int enqueue_finalize(mtm_handle *h, int n_c, double alpha, double *params, int mode, int n_steps, int R = 1,
+                     int variant = 0) {
     const mtm_data &dt = h->data;
     FinalizeArgs f{};
+    f.variant = variant;
+    f.nanmean = variant ? h->d_nanmean : nullptr;
     f.stats = h->d_statsbuf;
     f.n_c = n_c;
     f.d = dt.d;
@@ -467,6 +483,7 @@ int mtm_destroy(mtm_handle *h) {
     cudaFree(h->d_rng);
     cudaFreeHost(h->h_rng);
     cudaFree(h->d_pivot);
+    cudaFree(h->d_nanmean);
     cudaFree(h->d_ctrl);
     cudaFreeHost(h->h_ctrl);
     cudaFree(h->d_partials);
@@ -826,6 +843,90 @@ int mtm_em_fit(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assig
     if (switches_host && switches_cap > 0 && c.n_e_steps > 0) {
         const int m = c.n_e_steps < switches_cap ? c.n_e_steps : switches_cap;
         static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+        MTM_CUDA(h, cudaMemcpyAsync(switches_host, h->d_hist, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, h->stream));
+        MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int mtm_mstep_ext(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, double *params_dev,
+                  mtm_estep_info *info) {
+    if (!h) return -1;
+    if (!h->has_data) return fail(h, -1, "no resident data set (mtm_set_data)");
+    if (int rc = check_dims(h, &h->data, n_c)) return rc;
+    if (!assign_dev || !params_dev) return fail(h, -1, "NULL argument");
+    if (h->comm) return fail(h, -1, "mtm_mstep_ext is not sharded: detach the communicator");
+    if (h->data.ld != 0 && h->data.ld != h->data.n) return fail(h, -1, "mtm_mstep_ext needs a contiguous resident set");
+    DeviceGuard g(h->device);
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    if (int rc = enqueue_stats(h, assign_dev, n_c, 0, 0)) return rc;
+    if (int rc = enqueue_nanmean(h, assign_dev, n_c, 0)) return rc;
+    if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 0, 0, 1, 1)) return rc;
+    if (info) {
+        if (int rc = read_ctrl(h)) return rc;
+        info->n_switches = 0;
+        info->min_count = h->h_ctrl->min_count;
+        info->status = h->h_ctrl->status;
+        info->reserved = 0;
+    }
+    return 0;
+}
+
+int mtm_em_fit_ext(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assign_dev, int32_t *assign_prev_dev,
+                   double *params_dev, mtm_fit_info *info, int64_t *switches_host, int switches_cap) {
+    if (!h) return -1;
+    if (!h->has_data) return fail(h, -1, "no resident data set (mtm_set_data)");
+    if (int rc = check_dims(h, &h->data, n_c)) return rc;
+    if (!assign_dev || !assign_prev_dev || !params_dev || !info) return fail(h, -1, "NULL argument");
+    if (n_steps < 0) return fail(h, -1, "n_steps < 0");
+    if (h->comm) return fail(h, -1, "mtm_em_fit_ext is not sharded: detach the communicator");
+    if (h->data.ld != 0 && h->data.ld != h->data.n) return fail(h, -1, "mtm_em_fit_ext needs a contiguous resident set");
+    DeviceGuard g(h->device);
+    const mtm_data &dt = h->data;
+    if (n_steps > h->hist_cap) {
+        if (h->d_hist) MTM_CUDA(h, cudaFree(h->d_hist));
+        h->d_hist = nullptr;
+        h->hist_cap = 0;
+        MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->d_hist), sizeof(long long) * n_steps));
+        h->hist_cap = n_steps;
+    }
+    MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    MTM_CUDA(h, launch_copy_labels(assign_prev_dev, assign_dev, dt.n, h->d_ctrl, 0, h->stream));
+    h->launches += 1;
+    // first M-step (SSMM:263): no guard in front of it
+    if (int rc = enqueue_stats(h, assign_dev, n_c, 0, 0)) return rc;
+    if (int rc = enqueue_nanmean(h, assign_dev, n_c, 0)) return rc;
+    if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 1, n_steps, 1, 1)) return rc;
+    const int batch = ((double)dt.n * n_c < 2e6) ? 16 : 2;
+    int issued = 0;
+    if (int rc = read_ctrl(h)) return rc;
+    while (!h->h_ctrl->done && issued < n_steps) {
+        const int nb = (n_steps - issued < batch) ? (n_steps - issued) : batch;
+        for (int b = 0; b < nb; ++b) {
+            // keep the labels this E-step starts from: they stay the model's labels if the step is discarded
+            MTM_CUDA(h, launch_copy_labels(assign_prev_dev, assign_dev, dt.n, h->d_ctrl, 1, h->stream));
+            h->launches += 1;
+            if (int rc = enqueue_e_and_stats(h, n_c, params_dev, assign_dev, 1)) return rc;
+            if (int rc = enqueue_nanmean(h, assign_dev, n_c, 1)) return rc;
+            if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 1, n_steps, 1, 1)) return rc;
+        }
+        issued += nb;
+        if (int rc = read_ctrl(h)) return rc;
+    }
+    const Ctrl &c = *h->h_ctrl;
+    info->exit_code = c.exit_code;
+    info->n_e_steps = c.n_e_steps;
+    info->status = c.status;
+    info->n_m_steps = c.n_m_steps;
+    info->last_switches = c.last_switches;
+    info->min_count = c.min_count;
+    if (c.exit_code == MTM_EXIT_EMPTY || c.exit_code == MTM_EXIT_ERROR) {
+        // the reference's _E_step raised before it stored anything: the previous labels stand
+        MTM_CUDA(h, cudaMemcpyAsync(assign_dev, assign_prev_dev, sizeof(int32_t) * dt.n, cudaMemcpyDeviceToDevice, h->stream));
+        MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    if (switches_host && switches_cap > 0 && c.n_e_steps > 0) {
+        const int m = c.n_e_steps < switches_cap ? c.n_e_steps : switches_cap;
         MTM_CUDA(h, cudaMemcpyAsync(switches_host, h->d_hist, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, h->stream));
         MTM_CUDA(h, cudaStreamSynchronize(h->stream));
     }

@@ -74,6 +74,10 @@ struct FinalizeArgs {
     long long *switch_hist;  // nullable; (R, n_steps)
     int R;                   // batched restarts: one block per restart; stats (R, n_vals + kTail), params (R, n_c, pstride)
     double pivot[2 * MTM_MAX_DIM];  // the point the moments in `stats` were taken about (zeros = raw moments)
+    // variant 1 = framework_extended semantics (mtm_mstep_ext / mtm_em_fit_ext): nanmean initial mean from
+    // `nanmean` (n_c, 2d) [sum | count per coordinate], 1e-6 ridge when alpha == 0, the loop rules of SSMM.fit
+    int variant;
+    const double *nanmean;
 };
 
 // peer-memory mailboxes of the one-shot all-reduce (p2p.cu); at most 16 ranks (one NVSwitch box)
@@ -113,6 +117,13 @@ cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStrea
 size_t pivot_scratch_doubles(int sm_count);
 cudaError_t launch_pivot_sums(const double *a, int64_t n, int64_t ld, int T, int w, int sm_count, double *scratch,
                               double *out16, cudaStream_t s);
+// per-cluster, per-coordinate [sum | count] of the non-NaN entries of z_1 (np.nanmean, SSLG:43-44): out (n_c, 2d);
+// scratch: nanmean_scratch_doubles() doubles
+size_t nanmean_scratch_doubles(int n_c, int d, int sm_count);
+cudaError_t launch_nanmean(const double *z, int64_t n, int d, const int32_t *assign, int n_c, int sm_count,
+                           double *scratch, double *out, const Ctrl *ctrl, int check_done, cudaStream_t s);
+cudaError_t launch_copy_labels(int32_t *dst, const int32_t *src, int64_t n, const Ctrl *ctrl, int check_done,
+                               cudaStream_t s);
 cudaError_t launch_counts(const int32_t *assign, int64_t n, int n_c, unsigned long long *counts, cudaStream_t s);
 cudaError_t launch_score_reduce(const double *partials, int grid, double *out2, int R, cudaStream_t s);
 cudaError_t run_fp64_peak(int reps, int sm_count, cudaStream_t s, double *tflops);

@@ -461,8 +461,9 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
             const long long sw = (long long)(tail ? tail[0] : 0.0);
             ctrl->min_count = (long long)mn;
             if (ctrl->n_m_steps == 0) {
-                // before the first M-step: only the near-empty-cluster guard (MMM:1328-1336)
-                if (mn <= 3.0) {
+                // before the first M-step: only the near-empty-cluster guard (MMM:1328-1336); the extended
+                // mixture has none (its caller re-draws such an initial assignment, SSMM:251-260)
+                if (a.variant == 0 && mn <= 3.0) {
                     ctrl->done = 1;
                     ctrl->exit_code = MTM_EXIT_GUARD0;
                     go = 0;
@@ -473,6 +474,13 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
                 // arrived) leaves un-reduced statistics behind: stop as well instead of iterating on them.
                 ctrl->done = 1;
                 ctrl->exit_code = MTM_EXIT_ERROR;
+                go = 0;
+            } else if (a.variant == 1 && mn <= 0.0) {
+                // extended mixture: its _E_step asserts that every cluster has a member BEFORE it stores the
+                // new labels or counts switches (SSMM:122-124); the exception ends the fit (SSMM:275-276)
+                ctrl->n_e_steps += 1;
+                ctrl->done = 1;
+                ctrl->exit_code = MTM_EXIT_EMPTY;
                 go = 0;
             } else {
                 if (a.switch_hist && ctrl->n_e_steps < a.n_steps) a.switch_hist[ctrl->n_e_steps] = sw;
@@ -503,6 +511,8 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
         const double *st = a.stats + (size_t)c * sstride;
         double *pr = a.params + (size_t)c * pstride;
         const double n_total = tail ? tail[1] : (double)a.n_total;
+        // util.regress (the extended components' least squares) carries a fixed 1e-6 ridge (util_state_space.py:33-61)
+        const double alpha_eff = (a.variant == 1 && !(a.alpha > 0.0)) ? 1e-6 : a.alpha;
         int status = 0;
         if (part == 0) {
             pr[0] = st[0] / n_total;  // pi_c = mean(assign == c)
@@ -513,6 +523,10 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
             for (int i = 0; i < d; ++i) {
                 m[i] = b1[1 + i] / n0;  // 0/0 = NaN for an empty sample, like np.mean
                 pr[1 + i] = a0.pivot[i] + m[i];
+            }
+            if (a.variant == 1) {  // np.nanmean per coordinate (SSLG:43-44); the covariance below is unchanged
+                const double *nm = a0.nanmean + ((size_t)r * n_c + c) * 2 * d;
+                for (int i = 0; i < d; ++i) pr[1 + i] = nm[i] / nm[d + i];
             }
             int o = 1 + d;
             double *S = pr + 1 + d;
@@ -526,11 +540,11 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
         } else if (part == 1) {
             double *A = pr + 1 + d + d * d, *G = A + d * d;
             const RegDims<D_, D_> rd{d, d};
-            status |= regress_from_moments(rd, st + 1 + F1, a.alpha, a0.pivot, a0.pivot, A, G);
+            status |= regress_from_moments(rd, st + 1 + F1, alpha_eff, a0.pivot, a0.pivot, A, G);
         } else {
             double *H = pr + 1 + d + 3 * d * d, *Lam = H + d * l;
             const RegDims<D_, L_> rd{d, l};
-            status |= regress_from_moments(rd, st + 1 + F1 + F2, a.alpha, a0.pivot, a0.pivot + MX, H, Lam);
+            status |= regress_from_moments(rd, st + 1 + F1 + F2, alpha_eff, a0.pivot, a0.pivot + MX, H, Lam);
         }
         if (status) atomicOr(&s_status, status);
     }
@@ -607,6 +621,102 @@ cudaError_t launch_pivot_sums(const double *a, int64_t n, int64_t ld, int T, int
     if (grid < 1) grid = 1;
     pivot_partial_kernel<<<grid, 256, 0, s>>>(a, n, ld, T, w, scratch);
     pivot_reduce_kernel<<<1, 32, 0, s>>>(scratch, grid, out16);
+    return cudaGetLastError();
+}
+
+// ---- framework_extended helpers ---------------------------------------------------------------------------------
+// np.nanmean of z_1 per cluster and coordinate as [sum | count] of the non-NaN entries (an inf counts, like numpy).
+// One warp per 32 trajectories; per cluster present in the warp a fixed-order shuffle reduction, lane 0 adds into
+// the warp's shared-memory row; warps, then blocks, are added in index order: the same bits every run.
+__global__ void __launch_bounds__(256) nanmean_partial_kernel(const double *__restrict__ z, int64_t n, int d,
+                                                              const int32_t *__restrict__ assign, int n_c,
+                                                              double *partials, const Ctrl *ctrl, int check_done) {
+    if (check_done && ctrl->done) return;
+    extern __shared__ double s_nm[];  // [8 warps][n_c][2d]
+    const int w2 = 2 * d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < 8 * n_c * w2; k += 256) s_nm[k] = 0.0;
+    __syncthreads();
+    double *mine = s_nm + (size_t)warp * n_c * w2;
+    const int64_t n_warp_tiles = (n + 31) / 32;
+    for (int64_t wt = (int64_t)blockIdx.x * 8 + warp; wt < n_warp_tiles; wt += (int64_t)gridDim.x * 8) {
+        const int64_t i = wt * 32 + lane;
+        const int lab = i < n ? assign[i] : -1;
+        double v[MX];
+        MTM_UNROLL
+        for (int j = 0; j < MX; ++j) v[j] = (j < d && i < n) ? __ldg(z + i * d + j) : qnan();
+        for (int c = 0; c < n_c; ++c) {
+            if (__ballot_sync(0xffffffffu, lab == c) == 0u) continue;  // warp-uniform
+            MTM_UNROLL
+            for (int j = 0; j < MX; ++j) {
+                if (j < d) {
+                    const bool use = (lab == c) && (v[j] == v[j]);
+                    double sm = use ? v[j] : 0.0, ct = use ? 1.0 : 0.0;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                        ct += __shfl_xor_sync(0xffffffffu, ct, o);
+                    }
+                    if (lane == 0) {
+                        mine[c * w2 + j] += sm;
+                        mine[c * w2 + d + j] += ct;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_c * w2; k += 256) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_nm[(size_t)w * n_c * w2 + k];
+        partials[(size_t)blockIdx.x * n_c * w2 + k] = t;
+    }
+}
+
+__global__ void nanmean_reduce_kernel(const double *__restrict__ partials, int grid, int n_vals, double *out,
+                                      const Ctrl *ctrl, int check_done) {
+    if (check_done && ctrl->done) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_vals) return;
+    double t = 0.0;
+    for (int b = 0; b < grid; ++b) t += partials[(size_t)b * n_vals + k];
+    out[k] = t;
+}
+
+static int nanmean_grid(int64_t n, int sm_count) {
+    const int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count * 4;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+size_t nanmean_scratch_doubles(int n_c, int d, int sm_count) { return (size_t)sm_count * 4 * n_c * 2 * d; }
+
+cudaError_t launch_nanmean(const double *z, int64_t n, int d, const int32_t *assign, int n_c, int sm_count,
+                           double *scratch, double *out, const Ctrl *ctrl, int check_done, cudaStream_t s) {
+    const int grid = nanmean_grid(n, sm_count);
+    const int n_vals = n_c * 2 * d;
+    const size_t smem = (size_t)8 * n_vals * sizeof(double);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(nanmean_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    nanmean_partial_kernel<<<grid, 256, smem, s>>>(z, n, d, assign, n_c, scratch, ctrl, check_done);
+    nanmean_reduce_kernel<<<(n_vals + 127) / 128, 128, 0, s>>>(scratch, grid, n_vals, out, ctrl, check_done);
+    return cudaGetLastError();
+}
+
+// labels before an E-step of the extended fit (kept so that a discarded E-step can be undone); honours `done`
+__global__ void copy_labels_kernel(int32_t *__restrict__ dst, const int32_t *__restrict__ src, int64_t n,
+                                   const Ctrl *ctrl, int check_done) {
+    if (check_done && ctrl->done) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+cudaError_t launch_copy_labels(int32_t *dst, const int32_t *src, int64_t n, const Ctrl *ctrl, int check_done,
+                               cudaStream_t s) {
+    int grid = (int)((n + 255) / 256);
+    if (grid > 1184) grid = 1184;
+    if (grid < 1) grid = 1;
+    copy_labels_kernel<<<grid, 256, 0, s>>>(dst, src, n, ctrl, check_done);
     return cudaGetLastError();
 }
 

@@ -252,6 +252,36 @@ class Engine:
                             last_switches=int(info.last_switches), min_count=int(info.min_count),
                             switches=[int(hist[k]) for k in range(min(cap, int(info.n_e_steps)))])
 
+    def mstep_ext(self, data: DeviceData, assign, n_c, alpha):
+        """Component-style fits (framework_extended's StateSpaceLinearGaussian.fit) of every label value in one pass
+        (mtm_mstep_ext).  Returns (params (n_c, stride), min_count, status)."""
+        self._sync_stream()
+        self.bind(data)
+        params = torch.empty((n_c, self.param_stride(data.d, data.l)), dtype=torch.float64, device=self.device)
+        info = C.EStepInfo()
+        self._chk(self.lib.mtm_mstep_ext(self.h, ctypes.c_void_p(assign.data_ptr()), n_c, float(alpha),
+                                         ctypes.c_void_p(params.data_ptr()), ctypes.byref(info)))
+        return params, int(info.min_count), int(info.status)
+
+    def em_fit_ext(self, data: DeviceData, assign, n_c, alpha, n_steps):
+        """The EM loop of framework_extended's StateSpaceMixtureModel.fit with linear-Gaussian components
+        (mtm_em_fit_ext): assign (int32 device tensor) is updated in place.  Returns (params, info dict)."""
+        self._sync_stream()
+        self.bind(data)
+        params = torch.full((n_c, self.param_stride(data.d, data.l)), float("nan"), dtype=torch.float64,
+                            device=self.device)
+        prev = torch.empty_like(assign)
+        info = C.FitInfo()
+        cap = max(1, int(n_steps))
+        hist = (ctypes.c_int64 * cap)()
+        self._chk(self.lib.mtm_em_fit_ext(self.h, n_c, float(alpha), int(n_steps), ctypes.c_void_p(assign.data_ptr()),
+                                          ctypes.c_void_p(prev.data_ptr()), ctypes.c_void_p(params.data_ptr()),
+                                          ctypes.byref(info), hist, cap))
+        return params, dict(exit_code=int(info.exit_code), exit=C.EXIT_NAMES.get(int(info.exit_code), "?"),
+                            n_e_steps=int(info.n_e_steps), n_m_steps=int(info.n_m_steps), status=int(info.status),
+                            last_switches=int(info.last_switches), min_count=int(info.min_count),
+                            switches=[int(hist[k]) for k in range(min(cap, int(info.n_e_steps)))])
+
     def em_step(self, data: DeviceData, assign, params, n_c, alpha, want_info=True):
         """One EM iteration on resident data (the reference's E_step(); M_step() pair): assign and params
         (device tensors) are updated in place.  Returns (n_switches, min_count, status) if want_info."""

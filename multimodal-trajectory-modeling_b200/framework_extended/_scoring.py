@@ -3,7 +3,7 @@
 When every component is this package's ``StateSpaceLinearGaussian`` the whole matrix comes from ONE E-step launch
 (each component = one parameter row with pi = 1) instead of one ``score`` call — one upload of the data and one
 launch — per component, as ``StateSpaceMixtureModel._E_step`` / ``predict_proba`` / ``score`` of the reference do
-(framework_extended/state_space_model_mixture.py:110-132, 406-474).  Any other component type falls back to its
+(framework_extended/state_space_model_mixture.py:110-132, 406-474).  Any other component type is asked for its
 own ``score``."""
 
 from __future__ import annotations
@@ -11,19 +11,22 @@ from __future__ import annotations
 import numpy as np
 
 from ..engine import DeviceData, Engine
-from .state_space_model_linear_gaussian import StateSpaceLinearGaussian
+from .state_space_model_linear_gaussian import StateSpaceLinearGaussian, check_status
+
+
+def all_linear_gaussian(models) -> bool:
+    return bool(models) and all(type(m) is StateSpaceLinearGaussian for m in models)
 
 
 def score_matrix(models, data, device=None) -> np.ndarray:
-    if models and all(type(m) is StateSpaceLinearGaussian for m in models):
+    if all_linear_gaussian(models):
         eng = Engine.get(device)
         dd = data if isinstance(data, DeviceData) else DeviceData(*map(np.atleast_3d, data), eng.device)
         packed = np.concatenate([m._packed(dd.d, dd.l) for m in models])
         res = eng.estep(dd, packed, len(models), dd.T, want_ll=True)
-        if res["status"] & 1:
-            raise np.linalg.LinAlgError("Array must not contain infs or NaNs.")
-        return res["ll"].cpu().numpy()
+        check_status(res["status"])  # every failure bit, like the mixture class
+        return dd.from_resident(res["ll"]).cpu().numpy()
     if isinstance(data, DeviceData):
-        data = (data.z.cpu().numpy(), data.x.cpu().numpy())
+        data = (data.from_resident(data.z).cpu().numpy(), data.from_resident(data.x).cpu().numpy())
     states, measurements = map(np.atleast_3d, data)
     return np.stack([np.asarray(m.score((states, measurements))) for m in models])

@@ -130,22 +130,6 @@ def test_headline_kernel_keeps_uniform_parameter_operands():
         assert n_u >= 80 and n_u > 2 * n_v, (kern, n_u, n_v)
 
 
-def test_lg_component_fit_matches_reference():
-    """framework_extended.StateSpaceLinearGaussian.fit (host numpy restatement) against the
-    reference's fitted parameters (tests/golden/lg_component.npz)."""
-    from mtm_b200.framework_extended import state_space_model_linear_gaussian as ssm_lg
-
-    g = np.load(os.path.join(ROOT, "tests", "golden", "lg_component.npz"))
-    for tag in ("a0", "a1"):
-        mdl = ssm_lg.StateSpaceLinearGaussian(alpha=float(g[f"{tag}_alpha"])).fit((g[f"{tag}_z"], g[f"{tag}_x"]))
-        for got, key in ((mdl.state_init["mean"], "mean"), (mdl.state_init["cov"], "cov"),
-                         (mdl.state_model["coeff"], "A"), (mdl.state_model["covar"], "G"),
-                         (mdl.measurement_model["coeff"], "H"), (mdl.measurement_model["covar"], "L")):
-            assert np.allclose(got, g[f"{tag}_{key}"], rtol=1e-9, atol=1e-12), (tag, key)
-        back = ssm_lg.StateSpaceLinearGaussian().from_pickle(mdl.to_pickle())
-        assert np.array_equal(back.state_model["coeff"], mdl.state_model["coeff"]) and back.alpha == mdl.alpha
-
-
 def test_import_as_reference_package_name():
     """with the package directory first on sys.path the reference's own import line
     `from framework import marginalizable_mixture_model as mixmodel` resolves to the drop-in class."""

@@ -489,6 +489,23 @@ def test_lg_component_score():
         assert relerr(mdl.score((g[f"{tag}_zt"], g[f"{tag}_xt"])), g[f"{tag}_score_t"]) < RTOL
 
 
+def test_lg_component_fit_matches_reference():
+    """framework_extended.StateSpaceLinearGaussian.fit on the device (mtm_mstep_ext with one label: nanmean initial
+    mean, 1e-6-ridge / Ridge regressions) against the reference's fitted parameters
+    (tests/golden/lg_component.npz)."""
+    from mtm_b200.framework_extended import state_space_model_linear_gaussian as ssm_lg
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lg_component.npz"))
+    for tag in ("a0", "a1"):
+        mdl = ssm_lg.StateSpaceLinearGaussian(alpha=float(g[f"{tag}_alpha"])).fit((g[f"{tag}_z"], g[f"{tag}_x"]))
+        for got, key in ((mdl.state_init["mean"], "mean"), (mdl.state_init["cov"], "cov"),
+                         (mdl.state_model["coeff"], "A"), (mdl.state_model["covar"], "G"),
+                         (mdl.measurement_model["coeff"], "H"), (mdl.measurement_model["covar"], "L")):
+            assert relerr(got, g[f"{tag}_{key}"]) < RTOL, (tag, key)
+        back = ssm_lg.StateSpaceLinearGaussian().from_pickle(mdl.to_pickle())
+        assert np.array_equal(back.state_model["coeff"], mdl.state_model["coeff"]) and back.alpha == mdl.alpha
+
+
 def test_device_random_labels_bit_exact(eng):
     """mtm_random_labels == np.random.default_rng(seed).integers(0, n_c, n) bit for bit (MMM:166-168),
     including streams in which numpy's Lemire rejection fires (every later element shifts by one draw)."""
@@ -698,6 +715,19 @@ def test_extended_mixture_and_classifier(g_ext, tmp_path):
         assert relerr(pp, g[f"{tag}_proba_te"]) < RTOL and relerr(pn, g[f"{tag}_prenorm_te"]) < RTOL
         assert np.array_equal(mdl.predict(data=(zte, xte), letters=False), g[f"{tag}_pred_te"])
         assert relerr(mdl.cluster_assignment_index(cluster="B", data=(zte, xte)), g[f"{tag}_index_te"]) < RTOL
+    # the loop ran on the device with the extended class's own stopping rules
+    assert mdl.fit_info["exit"] in ("converged", "guard", "exhausted", "empty") and mdl.fit_info["n_m_steps"] >= 1
+    # E/M stepping through the class methods agrees with the device-resident loop
+    step = xm.StateSpaceMixtureModel(n_clusters=2, data=(np.where(np.isnan(ztr), 0.0, ztr), xtr),
+                                     component_model=xl.StateSpaceLinearGaussian, rng=np.random.default_rng(3))
+    step.cluster_assignment = step._initial_labels("k-means-all")
+    step._M_step()
+    for _ in range(50):
+        if step._E_step() == 0:
+            break
+        step._M_step()
+    assert np.array_equal(step.cluster_assignment, g["km_assign"])
+    assert relerr(step.cluster_models[0].state_model["coeff"], g["km_A0"]) < RTOL
     clf = xc.StateSpaceModelClassifier(component_model=xl.StateSpaceLinearGaussian).fit(data=(ztr, xtr), labels=g["lab_tr"])
     assert abs(clf.score() - float(g["clf_score"])) < RTOL * abs(float(g["clf_score"]))
     assert abs(clf.score(data=(zte, xte)) - float(g["clf_score_te"])) < RTOL * abs(float(g["clf_score_te"]))
