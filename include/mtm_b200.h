@@ -268,6 +268,30 @@ int mtm_p2p_attach(mtm_handle *h, const void *handles_all, int world_size, int r
 int mtm_random_labels(mtm_handle *h, const uint64_t pcg_state[4], int n_c, int64_t n, int32_t *assign_dev,
                       int *n_rejected_host);
 
+/* ---- k-means initial assignment on the device ------------------------------------------------------
+ * The reference's init="kmeans" (MMM:132-151): sklearn.cluster.KMeans(n_clusters, init="k-means++",
+ * random_state=seed).fit_predict on the FIRST NON-NULL STATE of every trajectory (first step whose d coordinates
+ * are all finite, step 0 if there is none; remaining NaN -> column mean).  Same algorithm as sklearn's
+ * (column-centred features, k-means++ seeding with 2 + log(k) local trials, Lloyd until no label changes or
+ * the squared centre shift is <= rel_tol * mean column variance, final labelling), driven by the SAME random
+ * numbers: the caller draws them from numpy's RandomState(seed) exactly as sklearn would —
+ *   first_center = rs.choice(n, p = 1/n);   u_host[(c-1) * n_trials + l] = rs.uniform(size = n_trials)[l]  per centre c >= 1
+ * — so the device start coincides with sklearn's up to rounding-level ties.
+ *   data        resident set (z_dev required); perm_dev: its pattern-order permutation or NULL — seeding follows
+ *               the CALLER's trajectory order, like sklearn on the caller's array
+ *   assign_dev  (n) int32 out, in the order of `data`
+ * Synchronises.  Not sharded. */
+typedef struct {
+    int32_t n_iter;        /* Lloyd iterations run */
+    int32_t converged;     /* 1 = no label changed, 2 = centre shift <= tol, 0 = max_iter reached */
+    int32_t empty_cluster; /* a cluster lost all members at some iteration (its centre was kept) */
+    int32_t reserved;
+    double tol;            /* absolute tolerance used */
+} mtm_kmeans_info;
+int mtm_kmeans_init(mtm_handle *h, const mtm_data *data, const int64_t *perm_dev, int n_c, int64_t first_center,
+                    const double *u_host, int n_trials, int max_iter, double rel_tol, int32_t *assign_dev,
+                    mtm_kmeans_info *info);
+
 /* ---- pattern-ordered residency --------------------------------------------------------------------
  * The reference keeps trajectories in the caller's order (MMM:75-81).  For a resident training set the
  * E-step is faster when every aligned group of 32 trajectories shares its per-step pattern of missing
@@ -290,6 +314,14 @@ int mtm_permute_f64(mtm_handle *h, const double *src_dev, double *dst_dev, int64
                     const int64_t *perm_dev, int inverse);
 int mtm_permute_i32(mtm_handle *h, const int32_t *src_dev, int32_t *dst_dev, int64_t rows, int64_t n,
                     const int64_t *perm_dev, int inverse);
+
+/* ---- cache key of a large data set -----------------------------------------------------------------
+ * The reference names its model cache after an md5 over all data bytes (MMM:177-188): ~10 s of host time for
+ * config 3's 5 GB.  mtm_fingerprint is the device-side stand-in: a 128-bit key of the data set (element values
+ * and their positions in the CALLER's order; perm_dev = the resident order's permutation or NULL), one pass at
+ * HBM speed, independent of the storage order and of the reduction order.  data->z_dev may be NULL.
+ * key_host: 2 x uint64 out.  Synchronises.  Not cryptographic; the reference's md5 stays available on the host. */
+int mtm_fingerprint(mtm_handle *h, const mtm_data *data, const int64_t *perm_dev, uint64_t key_host[2]);
 
 /* ---- measurement ---------------------------------------------------------------------------------
  * DFMA-saturating micro-kernel: FP64 peak of this device in TFLOP/s (FMA = 2 flop), best of `reps`,

@@ -42,6 +42,11 @@ class EStepInfo(ctypes.Structure):
                 ("reserved", ctypes.c_int32)]
 
 
+class KMeansInfo(ctypes.Structure):
+    _fields_ = [("n_iter", ctypes.c_int32), ("converged", ctypes.c_int32), ("empty_cluster", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("tol", ctypes.c_double)]
+
+
 class FitInfo(ctypes.Structure):
     _fields_ = [("exit_code", ctypes.c_int32), ("n_e_steps", ctypes.c_int32), ("status", ctypes.c_int32),
                 ("n_m_steps", ctypes.c_int32), ("last_switches", ctypes.c_int64), ("min_count", ctypes.c_int64)]
@@ -82,6 +87,9 @@ SIGNATURES = {
     "mtm_pattern_order": (_i, [_vp, ctypes.POINTER(MtmData), _vp]),
     "mtm_permute_f64": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _vp, _i]),
     "mtm_permute_i32": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i]),
+    "mtm_kmeans_init": (_i, [_vp, ctypes.POINTER(MtmData), _vp, _i, _i64, ctypes.POINTER(_d), _i, _i, _d, _vp,
+                             ctypes.POINTER(KMeansInfo)]),
+    "mtm_fingerprint": (_i, [_vp, ctypes.POINTER(MtmData), _vp, ctypes.POINTER(ctypes.c_uint64)]),
     "mtm_fp64_peak": (_i, [_vp, _i, ctypes.POINTER(_d)]),
     "mtm_launch_count": (_i64, [_vp]),
 }

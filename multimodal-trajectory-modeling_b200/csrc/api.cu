@@ -1235,6 +1235,76 @@ int mtm_permute_i32(mtm_handle *h, const int32_t *src_dev, int32_t *dst_dev, int
     return 0;
 }
 
+int mtm_kmeans_init(mtm_handle *h, const mtm_data *data, const int64_t *perm_dev, int n_c, int64_t first_center,
+                    const double *u_host, int n_trials, int max_iter, double rel_tol, int32_t *assign_dev,
+                    mtm_kmeans_info *info) {
+    if (!h || !data || !assign_dev || !info) return -1;
+    if (!data->z_dev) return fail(h, -1, "mtm_kmeans_init needs hidden states (z_dev)");
+    if (data->n < 1 || data->T < 1 || data->d < 1 || data->d > MTM_MAX_DIM) return fail(h, -1, "bad data shape");
+    if (n_c < 1 || n_c > MTM_MAX_CLUSTERS || n_c > data->n) return fail(h, -1, "n_c=%d out of range", n_c);
+    if (first_center < 0 || first_center >= data->n) return fail(h, -1, "first_center out of range");
+    if (n_c > 1 && (!u_host || n_trials < 1)) return fail(h, -1, "k-means++ needs the uniform draws");
+    if (h->comm) return fail(h, -1, "mtm_kmeans_init is not sharded: detach the communicator");
+    DeviceGuard g(h->device);
+    const int64_t n = data->n;
+    const int w = data->d;
+    const size_t rows_d = (size_t)n * w;
+    const size_t total = 2 * rows_d + kmeans_scratch_doubles(n, w, n_c, h->sm_count) + (size_t)n_c * w + (n + 1) / 2 + 8;
+    double *buf = nullptr;
+    MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&buf), total * sizeof(double)));
+    struct Free {  // scratch is released on every exit path
+        void *p;
+        ~Free() { cudaFree(p); }
+    } free_buf{buf};
+    double *rows_res = buf, *rows = buf + rows_d, *centers = rows + rows_d, *scratch = centers + (size_t)n_c * w;
+    int32_t *labels = reinterpret_cast<int32_t *>(scratch + kmeans_scratch_doubles(n, w, n_c, h->sm_count));
+    MTM_CUDA(h, launch_first_rows(data->z_dev, n, data->ld > 0 ? data->ld : n, data->T, w, rows_res, h->sm_count, h->stream));
+    h->launches += 1;
+    if (perm_dev) {  // seeding works on the caller's order
+        MTM_CUDA(h, launch_permute_f64(rows_res, rows, 1, n, w, perm_dev, 1, h->stream));
+        h->launches += 1;
+    } else {
+        MTM_CUDA(h, cudaMemcpyAsync(rows, rows_res, rows_d * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    int n_iter = 0, how = 0, empty = 0;
+    double tol = 0.0;
+    MTM_CUDA(h, run_kmeans(rows, n, w, n_c, first_center, u_host, n_trials, max_iter, rel_tol, labels, centers, scratch,
+                           h->sm_count, h->stream, &n_iter, &how, &empty, &tol, &h->launches));
+    if (perm_dev) {
+        MTM_CUDA(h, launch_permute_i32(labels, assign_dev, 1, n, perm_dev, 0, h->stream));
+        h->launches += 1;
+    } else {
+        MTM_CUDA(h, cudaMemcpyAsync(assign_dev, labels, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    info->n_iter = n_iter;
+    info->converged = how;
+    info->empty_cluster = empty;
+    info->reserved = 0;
+    info->tol = tol;
+    return 0;
+}
+
+int mtm_fingerprint(mtm_handle *h, const mtm_data *data, const int64_t *perm_dev, uint64_t key_host[2]) {
+    if (!h || !data || !key_host) return -1;
+    if (!data->x_dev || data->n < 1 || data->T < 1) return fail(h, -1, "bad data set");
+    if (data->ld != 0 && data->ld != data->n) return fail(h, -1, "mtm_fingerprint needs a contiguous data set");
+    DeviceGuard g(h->device);
+    if (int rc = ensure(h, h->d_score, h->score_cap, 8)) return rc;
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(h->d_score);
+    MTM_CUDA(h, cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), h->stream));
+    if (data->z_dev)
+        MTM_CUDA(h, launch_fingerprint(data->z_dev, data->T, data->n, data->d, perm_dev, 0x5a5a5a5aull, acc, h->sm_count,
+                                       h->stream));
+    MTM_CUDA(h, launch_fingerprint(data->x_dev, data->T, data->n, data->l, perm_dev, 0xc3c3c3c3ull, acc, h->sm_count,
+                                   h->stream));
+    h->launches += data->z_dev ? 2 : 1;
+    MTM_CUDA(h, cudaMemcpyAsync(h->h_pin, acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(key_host, h->h_pin, 2 * sizeof(uint64_t));
+    return 0;
+}
+
 int mtm_fp64_peak(mtm_handle *h, int reps, double *tflops_out) {
     if (!h || !tflops_out) return -1;
     DeviceGuard g(h->device);

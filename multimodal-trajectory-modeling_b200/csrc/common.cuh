@@ -142,6 +142,18 @@ cudaError_t launch_permute_f64(const double *src, double *dst, int64_t rows, int
 cudaError_t launch_permute_i32(const int32_t *src, int32_t *dst, int64_t rows, int64_t n, const int64_t *perm,
                                int inverse, cudaStream_t s);
 
+// k-means initial assignment (kmeans.cu)
+cudaError_t launch_first_rows(const double *z, int64_t n, int64_t ld, int T, int d, double *rows, int sm_count,
+                              cudaStream_t s);
+size_t kmeans_scratch_doubles(int64_t n, int w, int n_c, int sm_count);
+cudaError_t run_kmeans(double *rows, int64_t n, int w, int n_c, int64_t first_center, const double *u_host, int n_trials,
+                       int max_iter, double rel_tol, int32_t *labels, double *centers, double *scratch, int sm_count,
+                       cudaStream_t s, int *n_iter_out, int *how_out, int *empty_out, double *tol_out, int64_t *launches);
+
+// 128-bit order-independent key of a (T, n, w) array (misc.cu); out2 must be zeroed by the caller
+cudaError_t launch_fingerprint(const double *a, int64_t T, int64_t n, int w, const int64_t *perm,
+                               unsigned long long seed, unsigned long long *out2, int sm_count, cudaStream_t s);
+
 __host__ __device__ inline int param_stride(int d, int l) { return 1 + d + 3 * d * d + d * l + l * l; }
 // [N | n0, sum z (d), sum zz' (d(d+1)/2) | n1, sum u (2d), sum uu' (d(2d+1)) | n2, sum w (d+l), sum ww' ((d+l)(d+l+1)/2)]
 __host__ __device__ inline int stats_stride(int d, int l) {

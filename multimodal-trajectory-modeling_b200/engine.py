@@ -105,6 +105,20 @@ class DeviceData:
 class Engine:
     _cache: dict = {}
     _sharded: dict = {}
+    _local: dict = {}
+
+    @classmethod
+    def get_local(cls, device=None) -> "Engine":
+        """An engine of `device` that is guaranteed to carry NO communicator: Engine.get() itself unless user code
+        attached one to it (dist.attach(Engine.get(...))), else a private second handle.
+        Rank-local work of the classes (unsharded models, held-out data every rank holds in full, static regress)
+        must never be all-reduced."""
+        base = cls.get(device)
+        if base.world == 1:
+            return base
+        if base.device.index not in cls._local:
+            cls._local[base.device.index] = Engine(base.device)
+        return cls._local[base.device.index]
 
     @classmethod
     def get_sharded(cls, device=None, group=None) -> "Engine":
@@ -345,6 +359,36 @@ class Engine:
         self._chk(self.lib.mtm_random_labels(self.h, arr, int(n_c), int(n), ctypes.c_void_p(out.data_ptr()),
                                              ctypes.byref(rej)))
         return out, int(rej.value)
+
+    def kmeans_init(self, data: DeviceData, n_c, seed, max_iter=300, rel_tol=1e-4):
+        """The reference's init="kmeans" (MMM:132-151) on the device (mtm_kmeans_init): k-means of the first
+        non-null states, sklearn's algorithm on sklearn's random numbers — they are drawn here from numpy's
+        RandomState(seed) in the order sklearn draws them.  Returns (int32 labels in the order of `data`, info)."""
+        self._sync_stream()
+        n = data.n
+        rs = np.random.RandomState(seed)
+        first = int(rs.choice(n, p=np.full(n, 1.0) / float(n)))      # _kmeans_plusplus: first centre
+        n_trials = 2 + int(np.log(n_c))
+        u = np.ascontiguousarray(np.stack([rs.uniform(size=n_trials) for _ in range(1, n_c)]).ravel()
+                                 if n_c > 1 else np.zeros(1))
+        out = torch.empty(n, dtype=torch.int32, device=self.device)
+        info = C.KMeansInfo()
+        st = data.struct()
+        perm = ctypes.c_void_p(data.perm.data_ptr()) if data.perm is not None else None
+        self._chk(self.lib.mtm_kmeans_init(self.h, ctypes.byref(st), perm, int(n_c), first,
+                                           u.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_trials, int(max_iter),
+                                           float(rel_tol), ctypes.c_void_p(out.data_ptr()), ctypes.byref(info)))
+        return out, dict(n_iter=int(info.n_iter), converged=int(info.converged), empty_cluster=int(info.empty_cluster),
+                         tol=float(info.tol))
+
+    def fingerprint(self, data: DeviceData, d=None) -> str:
+        """32 hex digits: the device-side key of a data set in the caller's order (mtm_fingerprint)."""
+        self._sync_stream()
+        st = data.struct(d if d is not None else (data.d or 1))
+        key = (ctypes.c_uint64 * 2)()
+        perm = ctypes.c_void_p(data.perm.data_ptr()) if data.perm is not None else None
+        self._chk(self.lib.mtm_fingerprint(self.h, ctypes.byref(st), perm, key))
+        return f"{key[0]:016x}{key[1]:016x}"
 
     def fp64_peak(self, reps=10):
         self._sync_stream()

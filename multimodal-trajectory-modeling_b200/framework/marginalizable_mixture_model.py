@@ -113,7 +113,6 @@ class MMLinGaussSS_marginalizable:
         self.rng = np.random.default_rng(seed=self.random_seed)
         self.init = init
         self.alpha = alpha if alpha > 2 * np_eps else 0
-        self.cluster_assignment = self._initial_assignment()
 
         self._correspondence = dict(zip(range(k), string.ascii_uppercase))
         self.inverse_correspondence = {v: c for c, v in self._correspondence.items()}
@@ -131,6 +130,8 @@ class MMLinGaussSS_marginalizable:
         self._device = device
         self._data = _shared_data  # uploaded lazily
         self.fit_info = None       # dict from the last train(): exit, n_e_steps, switches, ...
+        self.kmeans_info = None    # dict from a k-means start computed on the device
+        self.cluster_assignment = self._initial_assignment()
 
     # ------------------------------------------------------------------ initial assignment
     def _initial_assignment(self):
@@ -138,6 +139,12 @@ class MMLinGaussSS_marginalizable:
         import sklearn.cluster as skl_cluster
 
         match self.init:
+            case "k-means" | "kmeans" if self._kmeans_on_device():
+                # large data: the same k-means (sklearn's algorithm on sklearn's random numbers, mtm_kmeans_init)
+                # on the resident set instead of a host KMeans over n rows
+                data = self._train_data()
+                labels, self.kmeans_info = self.engine.kmeans_init(data, self.n_clusters, self.random_seed)
+                return data.from_resident(labels).cpu().numpy().astype(np.int32)
             case "k-means" | "kmeans":
                 idx = np.argmax(np.isfinite(self.states).all(axis=2), axis=0).ravel()
                 first = self.states[idx, np.arange(self.n_data), :]
@@ -152,6 +159,13 @@ class MMLinGaussSS_marginalizable:
             case _:
                 return self.rng.integers(low=0, high=self.n_clusters, size=self.n_data)
 
+    def _kmeans_on_device(self) -> bool:
+        """k-means starts of large, unsharded sets run on the device; MTM_B200_KMEANS=device|host forces either."""
+        mode = os.environ.get("MTM_B200_KMEANS", "auto").lower()
+        if self._world > 1 or mode == "host" or not isinstance(self.random_seed, (int, np.integer)):
+            return False
+        return mode == "device" or self.n_data >= 200_000
+
     # ------------------------------------------------------------------ small properties
     @property
     def n_free_params(self) -> int:
@@ -164,18 +178,36 @@ class MMLinGaussSS_marginalizable:
 
     @property
     def hex_hash(self) -> str:
-        """md5 of states bytes + observations bytes + n_clusters (+ alpha), the reference's cache key
-        (MMM:177-188).  Same value as the reference; evaluated lazily because hashing a 10 M-trajectory data
-        set costs seconds and only the pickle cache needs it."""
+        """Cache key of (data, n_clusters, alpha), evaluated lazily — only the pickle cache needs it.
+
+        Small data: the reference's key, md5 of states bytes + observations bytes + n_clusters (+ alpha)
+        (MMM:177-188), so caches are interchangeable with the reference's.  Data of 64 MB and more (and not sharded):
+        the md5 is taken over the 128-bit device fingerprint of the resident data set (``mtm_fingerprint``, one pass
+        at HBM speed) instead of over 5 GB of host bytes; ``reference_hex_hash`` still gives the reference's key on
+        demand, ``MTM_B200_HASH=md5`` makes it the default again."""
         if self._hex_hash is None:
-            md5 = hashlib.md5()
-            md5.update(np.ascontiguousarray(self.states).data)
-            md5.update(np.ascontiguousarray(self.observations).data)
-            md5.update(str(self.n_clusters).encode("utf-8"))
-            if self.alpha > 2 * np_eps:
-                md5.update(np.format_float_positional(self.alpha, unique=True).encode("utf-8"))
-            self._hex_hash = md5.hexdigest()
+            big = (self.states.size + self.observations.size) * 8 >= (64 << 20)
+            if big and self._world == 1 and os.environ.get("MTM_B200_HASH", "fast").lower() != "md5":
+                md5 = hashlib.md5()
+                md5.update(b"mtm_b200-fingerprint:" + self.engine.fingerprint(self._train_data()).encode("ascii"))
+                self._hex_hash = self._hash_suffix(md5).hexdigest()
+            else:
+                self._hex_hash = self.reference_hex_hash
         return self._hex_hash
+
+    def _hash_suffix(self, md5):
+        md5.update(str(self.n_clusters).encode("utf-8"))
+        if self.alpha > 2 * np_eps:
+            md5.update(np.format_float_positional(self.alpha, unique=True).encode("utf-8"))
+        return md5
+
+    @property
+    def reference_hex_hash(self) -> str:
+        """md5 of states bytes + observations bytes + n_clusters (+ alpha): the reference's key (MMM:177-188)."""
+        md5 = hashlib.md5()
+        md5.update(np.ascontiguousarray(self.states).data)
+        md5.update(np.ascontiguousarray(self.observations).data)
+        return self._hash_suffix(md5).hexdigest()
 
     @hex_hash.setter
     def hex_hash(self, value: str) -> None:
@@ -196,10 +228,10 @@ class MMLinGaussSS_marginalizable:
         """The engine of the training set: with the group's communicator when the model is sharded."""
         if self._world > 1:
             return Engine.get_sharded(self._device, self._group if self._group is not False else None)
-        return Engine.get(self._device)
+        return Engine.get_local(self._device)
 
     def _engine_for(self, data) -> Engine:
-        return self.engine if getattr(data, "shard", None) else Engine.get(self._device)
+        return self.engine if getattr(data, "shard", None) else Engine.get_local(self._device)
 
     def _shard_of(self, n):
         """(lo, hi) of this rank for an n-trajectory set, or None if the set is not sharded."""
@@ -367,6 +399,61 @@ class MMLinGaussSS_marginalizable:
         data = self._resolve(states, observations)
         return self._estep(data, 1)["assign"].cpu().numpy().astype(np.int64)
 
+    # ---- per-visit snapshots without materialising them -------------------------------------------
+    def _snapshot_rows(self, s: int) -> np.ndarray:
+        """Parameter rows whose initial state is the model's marginal at time step s: (m A^s, V_s) with
+        V_0 = S, V_t = A' V_{t-1} A + Gamma (SSM:62-64, 312-314).  A one-step evaluation of x_s, z_s under such a
+        row is the likelihood of the trajectory whose every other step is missing."""
+        P = self._packed_params()
+        d = self.d_states
+        for c in range(self.n_clusters):
+            m, S = np.array(self.init_state_means[c], dtype=float).reshape(d), np.array(self.init_state_covs[c], dtype=float).reshape(d, d)
+            A, G = np.reshape(self.transition_matrices[c], (d, d)), np.reshape(self.transition_covs[c], (d, d))
+            for _ in range(s):
+                m, S = m @ A, A.T @ S @ A + G
+            P[c, 1:1 + d], P[c, 1 + d:1 + d + d * d] = m, S.ravel()
+        return P
+
+    def mle_cluster_assignment_snapshots(self, *, states, observations, return_probs: bool = False,
+                                         return_prenormalized_log_probs: bool = False, hidden_states: bool = True):
+        """``mle_cluster_assignment`` on the per-visit snapshots of (states, observations) — the n T pseudo-trajectories
+        ``util.parcellate_arrays`` builds (util/util_state_space.py:417-440; inference-adni-xval.py:194-221), each
+        with ONE time step present — without building them: snapshot s of all trajectories is one single-step
+        E-step launch on the views ``states[s]``, ``observations[s]`` under parameter rows whose initial state is
+        the model's marginal at step s.  T launches over n single steps instead of one launch over n T trajectories
+        of T steps.  Output layout = the parcellated call's: position s n + i is snapshot s of trajectory i.
+        ``hidden_states=False`` marginalises the hidden states (the call with ``np.nan * np.ones_like(z_parc)``)."""
+        states = np.atleast_3d(np.asarray(states, dtype=np.float64))
+        observations = np.atleast_3d(np.asarray(observations, dtype=np.float64))
+        eng = Engine.get_local(self._device)
+        full = DeviceData(states if hidden_states else None, observations, eng.device)
+        want_p = return_probs or return_prenormalized_log_probs
+        labels, probs, prenorm = [], [], []
+        for s in range(full.T):
+            view = DeviceData.__new__(DeviceData)
+            view.z = full.z[s:s + 1] if hidden_states else None
+            view.x, view.T, view.n, view.l, view.perm = full.x[s:s + 1], 1, full.n, full.l, None
+            view.d = full.d if hidden_states else None
+            res = eng.estep(view, self._snapshot_rows(s), self.n_clusters, 1, want_probs=want_p,
+                            want_prenorm=return_prenormalized_log_probs, d=self.d_states)
+            _raise_for_status(res["status"], self.alpha)
+            labels.append(res["assign"])
+            probs.append(res["probs"])
+            prenorm.append(res["prenorm"])
+        a = torch.cat(labels).cpu().numpy().astype(np.int64)
+        if not want_p:
+            return a
+        pr = torch.cat(probs, dim=1).cpu().numpy()
+        if not return_prenormalized_log_probs:
+            return a, pr
+        return a, pr, torch.cat(prenorm, dim=1).cpu().numpy()
+
+    def cluster_assignment_index_snapshots(self, *, cluster: str = "A", states, observations, hidden_states: bool = True):
+        """``cluster_assignment_index`` on the per-visit snapshots (see ``mle_cluster_assignment_snapshots``)."""
+        return self.mle_cluster_assignment_snapshots(
+            states=states, observations=observations, return_probs=True, return_prenormalized_log_probs=True,
+            hidden_states=hidden_states)[-1][self.inverse_correspondence[cluster]]
+
     # ---- observation-only route (hidden states marginalised) ------------------------------
     def _obs_data(self, observations):
         if observations is None:
@@ -493,7 +580,7 @@ class MMLinGaussSS_marginalizable:
             raise np.linalg.LinAlgError("Array must not contain infs or NaNs.")
         if X.shape[1] > C.MTM_MAX_DIM or Y.shape[1] > C.MTM_MAX_DIM:
             raise C.MtmError(f"regress: at most {C.MTM_MAX_DIM} regressors / responses on the device path")
-        eng = Engine.get()
+        eng = Engine.get_local()
         data = DeviceData(X[None], Y[None], eng.device)
         assign = torch.zeros(X.shape[0], dtype=torch.int32, device=eng.device)
         params, _, status = eng.mstep(data, assign, 1, alpha if alpha > 2 * np_eps else 0.0)

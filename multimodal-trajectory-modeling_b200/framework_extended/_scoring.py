@@ -20,7 +20,7 @@ def all_linear_gaussian(models) -> bool:
 
 def score_matrix(models, data, device=None) -> np.ndarray:
     if all_linear_gaussian(models):
-        eng = Engine.get(device)
+        eng = Engine.get_local(device)
         dd = data if isinstance(data, DeviceData) else DeviceData(*map(np.atleast_3d, data), eng.device)
         packed = np.concatenate([m._packed(dd.d, dd.l) for m in models])
         res = eng.estep(dd, packed, len(models), dd.T, want_ll=True)

@@ -32,7 +32,7 @@ class StateSpaceModelClassifier:
         self.class_models = [self.component_model() for _ in self.classes]
         members = [np.flatnonzero(index == k) for k in range(self.n_classes)]
         if self.component_model is StateSpaceLinearGaussian:
-            eng = Engine.get()
+            eng = Engine.get_local()
             dd = DeviceData(states, measurements, eng.device)
             lab = torch.from_numpy(index.astype(np.int32)).to(eng.device)
             params, _, status = eng.mstep_ext(dd, lab, self.n_classes, self.class_models[0].alpha)

@@ -66,7 +66,7 @@ class StateSpaceLinearGaussian:
     def fit(self, data):
         """all parameters from one pass over (states, measurements) on the device (SSLG:39-79)"""
         self.data = tuple(map(np.atleast_3d, data))
-        eng = Engine.get(self._device)
+        eng = Engine.get_local(self._device)
         dd = DeviceData(*self.data, eng.device)
         one = torch.zeros(dd.n, dtype=torch.int32, device=eng.device)
         params, _, status = eng.mstep_ext(dd, one, 1, self.alpha)
@@ -77,7 +77,7 @@ class StateSpaceLinearGaussian:
     def score(self, data=None):
         """log p(z_i, x_i) per trajectory, missing entries marginalised (SSLG:99-126)"""
         states, measurements = map(np.atleast_3d, self.data if data is None else data)
-        eng = Engine.get(self._device)
+        eng = Engine.get_local(self._device)
         dd = DeviceData(states, measurements, eng.device)
         res = eng.estep(dd, self._packed(dd.d, dd.l), 1, dd.T, want_ll=True)
         check_status(res["status"], self.alpha)

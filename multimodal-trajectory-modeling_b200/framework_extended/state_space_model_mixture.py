@@ -98,7 +98,7 @@ class StateSpaceMixtureModel:
 
     def _train_data(self) -> DeviceData:
         if self._resident is None:
-            self._resident = DeviceData(self.states, self.observations, Engine.get().device, pattern_order=True)
+            self._resident = DeviceData(self.states, self.observations, Engine.get_local().device, pattern_order=True)
         return self._resident
 
     def _ll(self, data=None) -> np.ndarray:
@@ -126,7 +126,7 @@ class StateSpaceMixtureModel:
         if self._on_device:
             data = self._train_data()
             lab = data.to_resident(np.ascontiguousarray(self.cluster_assignment, dtype=np.int32))
-            rows, _, _ = Engine.get().mstep_ext(data, lab, self.n_clusters, self.cluster_models[0].alpha)
+            rows, _, _ = Engine.get_local().mstep_ext(data, lab, self.n_clusters, self.cluster_models[0].alpha)
             self._adopt_rows(rows.cpu().numpy())
         else:
             for c, mdl in enumerate(self.cluster_models):
@@ -145,7 +145,7 @@ class StateSpaceMixtureModel:
         return changed
 
     def _em_on_device(self, n_iter: int):
-        eng, data = Engine.get(), self._train_data()
+        eng, data = Engine.get_local(), self._train_data()
         lab = data.to_resident(np.ascontiguousarray(self.cluster_assignment, dtype=np.int32))
         rows, self.fit_info = eng.em_fit_ext(data, lab, self.n_clusters, self.cluster_models[0].alpha, n_iter)
         self.cluster_assignment = data.from_resident(lab).cpu().numpy().astype(np.int64)

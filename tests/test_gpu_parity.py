@@ -212,6 +212,16 @@ def test_adni_fold(g_adni, mix):
     assert relerr(best.cluster_assignment_index(states=zp, observations=xp), g_adni["te_snap_index"]) < RTOL
     assert np.array_equal(best.mle_cluster_assignment(states=np.nan * np.ones_like(zp), observations=xp),
                           g_adni["te_snapx_assign"])
+    # the same snapshots without materialising the n T pseudo-trajectories (one single-step launch per visit)
+    a_s, pr_s, pn_s = best.mle_cluster_assignment_snapshots(states=zte, observations=xte, return_probs=True,
+                                                            return_prenormalized_log_probs=True)
+    a_m, pr_m, pn_m = best.mle_cluster_assignment(states=zp, observations=xp, return_probs=True,
+                                                  return_prenormalized_log_probs=True)
+    assert np.array_equal(a_s, g_adni["te_snap_assign"]) and np.array_equal(a_s, a_m)
+    assert relerr(pr_s, pr_m) < RTOL and relerr(pn_s, pn_m) < RTOL
+    assert relerr(best.cluster_assignment_index_snapshots(states=zte, observations=xte), g_adni["te_snap_index"]) < RTOL
+    assert np.array_equal(best.mle_cluster_assignment_snapshots(states=zte, observations=xte, hidden_states=False),
+                          g_adni["te_snapx_assign"])
     znh = np.nan * np.ones_like(zte)
     assert np.array_equal(best.mle_cluster_assignment(states=znh, observations=xte), g_adni["te_nohid_assign"])
     assert relerr(best.cluster_assignment_index(states=znh, observations=xte), g_adni["te_nohid_index"]) < RTOL
@@ -399,6 +409,63 @@ def test_pickle_roundtrip(mix, tmp_path):
     assert back.hex_hash == mdl.hex_hash
     assert np.array_equal(back._packed_params(), mdl._packed_params())
     assert np.array_equal(back.mle_cluster_assignment(), mdl.mle_cluster_assignment())
+
+
+def test_kmeans_start_on_device(g_restarts, mix, eng, monkeypatch):
+    """init="kmeans" on the device (mtm_kmeans_init): the golden sets' k-means starts (sklearn, MMM:132-151,
+    incl. the NaN -> column-mean imputation of set A) are reproduced label for label, and on a large synthetic set
+    the device start equals a host sklearn KMeans on the same features."""
+    import sklearn.cluster as skl_cluster
+
+    monkeypatch.setenv("MTM_B200_KMEANS", "device")
+    for tag in ("A", "B"):
+        z, x = g_restarts[f"{tag}_z"], g_restarts[f"{tag}_x"]
+        n_c = int(g_restarts[f"{tag}_meta"][4])
+        km = mix.MMLinGaussSS_marginalizable(n_clusters=n_c, states=z, observations=x, random_seed=0, init="kmeans")
+        assert km.kmeans_info is not None and km.kmeans_info["converged"] in (1, 2)
+        assert np.array_equal(km.cluster_assignment, g_restarts[f"{tag}_kmeans_assign0"]), tag
+    monkeypatch.setenv("MTM_B200_KMEANS", "auto")
+    n, T, d, l, n_c = 300_000, 4, 3, 2, 5
+    z, x = _synthetic(n, T, d, l, n_c, seed=13, sep=1.0)
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=n_c, states=z, observations=x, random_seed=7, init="kmeans")
+    assert mdl.kmeans_info is not None
+    idx = np.argmax(np.isfinite(z).all(axis=2), axis=0)
+    first = z[idx, np.arange(n), :]
+    first = np.where(np.isfinite(first), first, np.nanmean(first, axis=0, keepdims=True))
+    host = skl_cluster.KMeans(n_clusters=n_c, init="k-means++", random_state=7).fit_predict(first)
+    agree = float(np.mean(host == mdl.cluster_assignment))
+    assert agree > 0.9999, agree
+    assert np.array_equal(np.bincount(host, minlength=n_c) > 0, np.bincount(mdl.cluster_assignment, minlength=n_c) > 0)
+
+
+def test_fingerprint_cache_key(mix, eng, monkeypatch):
+    """mtm_fingerprint: the same key for the same data whatever the storage order, another key after a one-bit
+    change; the class uses it as cache key for large data and keeps the reference's md5 on demand."""
+    import hashlib
+
+    import mtm_b200
+
+    z, x = _synthetic(70_003, 8, 4, 4, 3, seed=5)
+    plain = mtm_b200.DeviceData(z, x, eng.device)
+    ordered = mtm_b200.DeviceData(z, x, eng.device, pattern_order=True)
+    k0, k1 = eng.fingerprint(plain), eng.fingerprint(ordered)
+    assert k0 == k1 and len(k0) == 32
+    z2 = z.copy()
+    z2[3, 777, 1] = np.nextafter(z2[3, 777, 1], np.inf) if np.isfinite(z2[3, 777, 1]) else 0.0
+    assert eng.fingerprint(mtm_b200.DeviceData(z2, x, eng.device)) != k0
+    zs = z.copy()
+    zs[:, [1, 2]] = zs[:, [2, 1]]  # two trajectories swapped: another data set
+    assert eng.fingerprint(mtm_b200.DeviceData(zs, x, eng.device)) != k0
+    mdl = mix.MMLinGaussSS_marginalizable(n_clusters=3, states=z, observations=x)
+    ref = hashlib.md5(z.tobytes() + x.tobytes() + b"3").hexdigest()
+    assert mdl.reference_hex_hash == ref and mdl.hex_hash == ref  # 36 MB: below the threshold, the reference's key
+    big_z, big_x = np.tile(z, (1, 2, 1)), np.tile(x, (1, 2, 1))
+    big = mix.MMLinGaussSS_marginalizable(n_clusters=3, states=big_z, observations=big_x)
+    assert len(big.hex_hash) == 32 and big.hex_hash != big.reference_hex_hash
+    again = mix.MMLinGaussSS_marginalizable(n_clusters=3, states=big_z.copy(), observations=big_x.copy())
+    assert again.hex_hash == big.hex_hash
+    monkeypatch.setenv("MTM_B200_HASH", "md5")
+    assert mix.MMLinGaussSS_marginalizable(n_clusters=3, states=big_z, observations=big_x).hex_hash == big.reference_hex_hash
 
 
 def test_batched_restarts_equal_sequential(mix, eng):
