@@ -95,11 +95,20 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
             reinterpret_cast<double *>(stats_base)[k] = 0.0;
     if (tid == 0) s_sw = 0;
     __syncthreads();
-    for (int c = tid; c < a.n_c; c += kEThreads) {
+    // per cluster: pi, log pi, finiteness masks of the unconditional mean (8 lanes per cluster, 16 clusters per pass)
+    for (int c0 = 0; c0 < a.n_c; c0 += kEThreads / 8) {
+        const int c_raw = c0 + (tid >> 3);
+        const bool c_ok = c_raw < a.n_c;
+        const int c = c_ok ? c_raw : a.n_c - 1;
         const auto src = PS::get(s_par, r * a.n_c + c, c, stride);
-        s_pi[c] = src[0];
-        s_logpi[c] = log(src[0]);
-        mean_finite_masks(dm, src, a.T0, s_fin + c * a.T0);
+        if (c_ok && (tid & 7) == 0) {
+            s_pi[c] = src[0];
+            s_logpi[c] = log(src[0]);
+        }
+        mean_finite_masks_lanes(dm, src, a.T0, s_fin + c * a.T0, c_ok);
+    }
+    __syncthreads();
+    for (int c = tid; c < a.n_c; c += kEThreads) {
         uint32_t any = 0;
         for (int t = 0; t < a.T0; ++t) any |= s_fin[c * a.T0 + t];
         s_live[c] = any;
