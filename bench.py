@@ -187,17 +187,6 @@ def flops_per_eval(T, d, l, kz_mean, kx_mean):
     return T * pred + (T - 1) * prop + kz_mean * per_z + kx_mean * per_x
 
 
-def flops_skipped_by_point_steps(T, d, l, n_point, n_point_not_last, kx_point):
-    """Part of flops_per_eval the kernel does NOT execute when a warp takes the point-mass shortcut
-    (all of z_t present for its 32 trajectories): the x-predictive covariance products and the (mu, P, C)
-    updates of that step work on an exactly zero covariance, and so does A'PA of the following propagation.
-    n_point = such steps per trajectory, kx_point = present x scalars in them."""
-    pred_cov = 2 * d * d * l + d * l * (l + 1)                    # C = P H and H'C
-    per_x = d + 2 * d + d * (d + 1) + 0.5 * (l - 1) * 2 * d       # gains, mu, P and C updates per present x scalar
-    prop_cov = 2 * d ** 3 + d * d * (d + 1)                       # P A and A'(PA)
-    return n_point * pred_cov + kx_point * per_x + n_point_not_last * prop_cov
-
-
 def flops_per_eval_survey(T, d, l, k_mean):
     """250 T + 250 (T-1) + 101 k at d = l = 4 (full (d+l)-dim rank-1 update per
     present scalar): the count of a less structured sequential algorithm, quoted for comparison."""
@@ -389,11 +378,9 @@ def data_stats(torch, z, x):
     n = x.shape[1]
     kx = float(torch.isfinite(x).sum().item()) / n
     if z is None:
-        return dict(kz=0.0, kx=kx, n_point=0.0, n_point_nl=0.0, kx_point=0.0)
+        return dict(kz=0.0, kx=kx)
     kz = float(torch.isfinite(z).sum().item()) / n
-    zc = torch.isfinite(z).all(dim=2)
-    out = dict(kz=kz, kx=kx, n_point=float(zc.sum().item()) / n, n_point_nl=float(zc[:-1].sum().item()) / n,
-               kx_point=float((torch.isfinite(x).sum(dim=2) * zc).sum().item()) / n)
+    out = dict(kz=kz, kx=kx)
     return out
 
 
@@ -519,22 +506,30 @@ class EmRunner:
                 "status": int(info.status), "cluster_sizes": sizes, "n_switches": int(sw.item())}
 
 
-def em_roofline(ctx, cfg, ds, n_loc, ms_e, ms_m, pattern_order, kernel):
+def em_roofline(ctx, cfg, ds, n_loc, ms_e, ms_m, pattern_order, kernel, wsc):
     T, d, l, n_c = cfg["T"], cfg["d"], cfg["l"], cfg["n_c"]
     f_eval = flops_per_eval(T, d, l, ds["kz"], ds["kx"])
     f_survey = flops_per_eval_survey(T, d, l, ds["kz"] + ds["kx"])
-    f_skip = flops_skipped_by_point_steps(T, d, l, ds["n_point"], ds["n_point_nl"], ds["kx_point"]) if pattern_order else 0.0
+    instr_eval = T * (162.0 * wsc["point"] + 264.0 * wsc["rank_one"] + 466.0 * wsc["generic"])
     evals = n_loc * n_c
     tf = f_eval * evals / (ms_e * 1e-3) * 1e-12
     bpt = bytes_per_traj(T, d, l)
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of THIS launch configuration
+    # (profiles/r2i_fused_ncu_summary.md: 5.168793 GB read = one pass over the data + labels, 112.1 MB written = new
+    # labels + 72 MB of block partials); any other size has no capture
+    captured = (n_loc == 10_000_000 and (T, d, l, n_c) == (8, 4, 4, 8) and pattern_order)
     return {"bound": "fp64", "achieved": tf, "peak": ctx.fp64_peak, "unit": "TFLOP/s", "frac": tf / ctx.fp64_peak,
-            "traffic": None, "kernel": kernel, "kernel_ms": ms_e, "flops_per_eval": f_eval,
+            "traffic": (5.168793e9 + 112.147968e6) if captured else None,
+            "traffic_unit": "bytes per launch (ncu capture of this configuration)" if captured else None,
+            "algorithmic_bytes": bpt * n_loc, "kernel": kernel, "kernel_ms": ms_e, "flops_per_eval": f_eval,
             "evals_per_launch": evals,
-            # the algorithmic count above is layout-independent; on the pattern-ordered resident set whole warps
-            # skip the zero-covariance arithmetic of the steps with a complete z_t, so the kernel EXECUTES less:
-            "flops_per_eval_executed": f_eval - f_skip,
-            "frac_executed": (f_eval - f_skip) * evals / (ms_e * 1e-3) * 1e-12 / ctx.fp64_peak,
-            "point_steps_per_trajectory": ds["n_point"],
+            # What the kernel EXECUTES: FP64 instructions per evaluation by code path (SASS counts of the time loop:
+            # point-mass step 162, rank-one step 264, generic step 466) weighted with the measured path mix of the
+            # resident order, and the FP64-pipe activity that implies (a warp instruction occupies an SM
+            # sub-partition's FP64 pipe for 2 cycles; ncu measured 57.5 % for this kernel, profiles/)
+            "fp64_instr_per_eval_model": instr_eval,
+            "fp64_pipe_active_model": instr_eval * evals / 32.0 * 2.0 / (148 * 4 * 1.965e9 * ms_e * 1e-3),
+            "warp_step_paths": wsc,
             "peak_source": "measured here: mtm_fp64_peak, the better of two DFMA micro-kernels, best of 10 each "
                            "(nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2; MEASURED_PEAKS.json has no fp64 entry)",
             "frac_of_nominal": tf / 37.2,
@@ -583,7 +578,7 @@ def leg_em(ctx, cfg, steps, warmup, tag, pattern_order=True):
            "roofline": em_roofline(ctx, cfg, ds, n_loc, ms_e, ms_m, pattern_order,
                                    "estep_kernel<4,4,HAS_Z=1,CONSTP=1> with the M-step statistics fused in (the "
                                    "timed span also holds the two ~10 us reduction kernels and, for N > 1, the "
-                                   "all-reduce)")}
+                                   "all-reduce)", wsc)}
     # state after the timed iteration: labels in the caller's order, gathered; Q and LL all-reduced by the library
     labels = ctx.gather_labels(run.data.from_resident(run.assign), n_total)
     q, ll, st = ctx.eng.score(run.data, run.params, n_c)

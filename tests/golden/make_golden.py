@@ -543,8 +543,41 @@ def golden_conditioning(ssm, mmm):
     print("conditioning.npz written")
 
 
+# ---------------------------------------------------------------------------
+# 8. model selection (model-selection.py:45-72)
+# ---------------------------------------------------------------------------
+
+
+def golden_model_selection(ssm, mmm):
+    """The loop of model-selection.py: for n_c in a range, the best of a k-means start and a few random starts,
+    then its AIC / BIC / Q / LL (MSEL:45-72), on a small 3-cluster data set with suffix-missing lengths."""
+    rng = np.random.default_rng(31337)
+    n, T, d, l = 900, 5, 2, 3
+    z, x, lab, comps = sample_mixture(ssm, rng, n, T, d, l, 3, 0.0, 0.8)
+    length = rng.integers(2, T + 1, size=n)
+    for i in range(n):
+        z[length[i]:, i, :] = np.nan
+        x[length[i]:, i, :] = np.nan
+    x[rng.random(x.shape) < 0.1] = np.nan
+    rows, n_starts = [], 4
+    out = dict(z=z, x=x, n_starts=n_starts)
+    for n_c in range(1, 5):
+        best = mmm.MMLinGaussSS_marginalizable(n_clusters=n_c, states=z, observations=x).train_with_multiple_random_starts(
+            n_starts=n_starts, n_steps=100, use_cache=False)
+        rows.append([n_c, best.aic(), best.bic(), best.e_complete_data_log_lik(), best.model_log_likelihood(),
+                     best.n_free_params, best.random_seed])
+        out[f"assign_{n_c}"] = np.array(best.cluster_assignment)
+        print("model selection n_c", n_c, rows[-1])
+    out["table"] = np.array(rows, dtype=float)
+    np.savez_compressed(os.path.join(HERE, "model_selection.npz"), **out)
+    print("model_selection.npz written")
+
+
 if __name__ == "__main__":
     ssm, mmm, uss = import_reference()
+    if "msel" in sys.argv[1:]:
+        golden_model_selection(ssm, mmm)
+        sys.exit(0)
     if "cond" in sys.argv[1:]:
         golden_conditioning(ssm, mmm)
         sys.exit(0)

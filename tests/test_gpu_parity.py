@@ -515,6 +515,22 @@ def test_model_selection_sweep(mix):
     assert table["Q"][2] > table["Q"][0]
 
 
+def test_model_selection_matches_reference(mix):
+    """model-selection.py:45-72 against the reference's own output (tests/golden/model_selection.npz): for every n_c
+    the same winner (seed, labels) and the same AIC / BIC / Q / LL / number of free parameters."""
+    from mtm_b200 import sweep
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_selection.npz"))
+    ref = g["table"]
+    table, models = sweep.select_n_clusters(g["z"], g["x"], range(1, 5), n_starts=int(g["n_starts"]), n_steps=100)
+    for k, n_c in enumerate(range(1, 5)):
+        assert models[n_c].random_seed == int(ref[k, 6]), n_c
+        assert np.array_equal(models[n_c].cluster_assignment, g[f"assign_{n_c}"]), n_c
+        assert table["n_free_params"][k] == ref[k, 5]
+        for col, name in ((1, "aic"), (2, "bic"), (3, "Q"), (4, "LL")):
+            assert relerr(table[name][k], ref[k, col]) < RTOL, (n_c, name)
+
+
 def test_host_streamed_step_equals_resident_step(eng):
     """mtm_em_step_host (slab-pipelined upload) == mtm_em_step on resident data: labels and switch count
     bit-exact, parameters to rounding (the block-partial grouping differs), for ragged slab sizes."""
