@@ -100,12 +100,13 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
         const int c_raw = c0 + (tid >> 3);
         const bool c_ok = c_raw < a.n_c;
         const int c = c_ok ? c_raw : a.n_c - 1;
-        const auto src = PS::get(s_par, r * a.n_c + c, c, stride);
+        const double *row = params + (size_t)c * stride;  // global memory on purpose, see mean_finite_masks_lanes
         if (c_ok && (tid & 7) == 0) {
-            s_pi[c] = src[0];
-            s_logpi[c] = log(src[0]);
+            const double pi_c = __ldg(row);
+            s_pi[c] = pi_c;
+            s_logpi[c] = log(pi_c);
         }
-        mean_finite_masks_lanes(dm, src, a.T0, s_fin + c * a.T0, c_ok);
+        mean_finite_masks_lanes(dm, row, a.T0, s_fin + c * a.T0, c_ok);
     }
     __syncthreads();
     for (int c = tid; c < a.n_c; c += kEThreads) {

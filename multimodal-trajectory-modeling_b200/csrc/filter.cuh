@@ -722,29 +722,40 @@ __device__ void mean_finite_masks(const DM &dm, const PS &psrc, int T0, uint32_t
 }
 
 // The same masks, eight lanes per cluster (lane j = state coordinate j and observation coordinate j): the sums run in
-// the same order as above, so the masks are identical; a block's prologue costs a fraction of a microsecond instead
-// of the several a single thread with run-time-indexed local arrays took (with ~2 tiles per block on a 1.25 M
-// shard — 8 GPUs — that was percent of the launch).  Every lane of the warp must call it; `c_ok` = this 8-lane
-// group's cluster exists (the others compute on a clamped cluster and write nothing).
-template <class DM, class PS>
-__device__ __forceinline__ void mean_finite_masks_lanes(const DM &dm, const PS &psrc, int T0, uint32_t *fin, bool c_ok) {
-    const ParamView<DM, PS> p(dm, psrc);
+// the same order as above, so the masks are identical.  The lane's columns of A and H are read ONCE, from the
+// parameter rows in GLOBAL memory: lanes of one warp want different parameters, and a constant-bank load with 32
+// different addresses is replayed 32 times — the one-thread-per-cluster prologue and a first lane-parallel version
+// that still read the constant bank both cost ~10 us per block (ncu: 0.7 % of a launch with 15 tiles per block,
+// 5 % with the 2 tiles per block of a 1.25 M shard on 8 GPUs).  Every lane of the warp must call it; `c_ok` = this
+// 8-lane group's cluster exists (the others compute on a clamped cluster and write nothing).
+template <class DM>
+__device__ __forceinline__ void mean_finite_masks_lanes(const DM &dm, const double *__restrict__ row, int T0,
+                                                        uint32_t *fin, bool c_ok) {
+    const ParamView<DM, SmemSrc> p(dm, SmemSrc{row});
     const int d = dm.d(), l = dm.l();
     const int lane = threadIdx.x & 31, j = lane & 7, base = lane & 24;
-    double mu = j < d ? p.m(j) : 0.0;
+    double a_col[MTM_MAX_DIM], h_col[MTM_MAX_DIM];
+    MTM_UNROLL
+    for (int i = 0; i < MTM_MAX_DIM; ++i) {
+        a_col[i] = (i < d && j < d) ? __ldg(row + p.oA + i * d + j) : 0.0;
+        h_col[i] = (i < d && j < l) ? __ldg(row + p.oH + i * l + j) : 0.0;
+    }
+    double mu = j < d ? __ldg(row + 1 + j) : 0.0;
     for (int t = 0; t < T0; ++t) {
         if (t > 0) {
             double s = 0.0;
-            for (int i = 0; i < d; ++i) {
+            MTM_UNROLL
+            for (int i = 0; i < MTM_MAX_DIM; ++i) {
                 const double mi = __shfl_sync(0xffffffffu, mu, base + i);
-                if (j < d) s = fma(mi, p.A(i * d + j), s);
+                if (i < d) s = fma(mi, a_col[i], s);
             }
             mu = s;
         }
         double sx = 0.0;
-        for (int i = 0; i < d; ++i) {
+        MTM_UNROLL
+        for (int i = 0; i < MTM_MAX_DIM; ++i) {
             const double mi = __shfl_sync(0xffffffffu, mu, base + i);
-            if (j < l) sx = fma(mi, p.H(i * l + j), sx);
+            if (i < d) sx = fma(mi, h_col[i], sx);
         }
         const uint32_t zb = (__ballot_sync(0xffffffffu, j < d && finite_bits(mu)) >> base) & 0xffu;
         const uint32_t xb = (__ballot_sync(0xffffffffu, j < l && finite_bits(sx)) >> base) & 0xffu;

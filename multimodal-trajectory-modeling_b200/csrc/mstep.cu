@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kSThreads) stats_kernel(const StatsArgs a) {
         const int64_t i_raw = tile * kSThreads + tid;
         const bool valid = i_raw < n;
         const int64_t i = valid ? i_raw : n - 1;
-        stats_tile(dm, a.z, a.x, a.ld, a.T, i, valid ? assign[i] : -1, n_c, smem_raw, a.pivot);
+        stats_tile<DM, true>(dm, a.z, a.x, a.ld, a.T, i, valid ? assign[i] : -1, n_c, smem_raw, a.pivot);
     }
     __syncthreads();
     double *out = a.partials + 2 * ((size_t)r * gridDim.x + blockIdx.x) * n_c * sstride;

@@ -129,7 +129,10 @@ __device__ __forceinline__ void centre_row(double (&v)[NM], int n, const double 
 // One tile.  Every thread of the block must call it (it synchronises); `label` is the cluster of
 // trajectory i (any value outside [0, n_c) = not counted), `i` a valid (clamped) trajectory index.
 // piv: [z pivot (at 0) | x pivot (at MTM_MAX_DIM)], kernel-parameter space (uniform loads).
-template <class DM>
+// PREFETCH (stand-alone statistics kernel only): the rows come from HBM and every load below is consumed where it
+// is issued — ask for all 2T rows of the trajectory up front.  In the fused E-step the rows are in L2 / L1 already
+// (the same prefetches there measured 0.2 % slower) and its code must not change shape, so it is a template flag.
+template <class DM, bool PREFETCH = false>
 __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restrict__ z, const double *__restrict__ x,
                                            int64_t ld, int T, int64_t i, int label, int n_c, unsigned char *smem_base,
                                            const double *piv) {
@@ -182,6 +185,12 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
 
     const double *z_i = z + i * d;
     const double *x_i = x + i * l;
+    if (PREFETCH) {
+        for (int t = 0; t < T; ++t) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(z_i + (int64_t)t * zs));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(x_i + (int64_t)t * xs));
+        }
+    }
 
     // NOTE: the two passes deliberately load each step right before its use.  A one-step-ahead software
     // prefetch here (tried) made ptxas 12.9 drop the uniform-datapath parameter operands of the E-step time
