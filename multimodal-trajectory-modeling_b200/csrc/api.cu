@@ -248,7 +248,7 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
     return 0;
 }
 
-constexpr int kP2PCap = 16384;  // doubles per rank and parity in a mailbox (128 KB): n_c * 106 + 2 fits for n_c <= 64
+constexpr int kP2PCap = 65536;  // doubles per rank and parity in a mailbox (512 KB): 32 batched restarts at n_c = 12 (40 832) fit
 
 int allreduce_stats(mtm_handle *h, double *buf, size_t count, int R = 1) {
     if (!h->comm) return 0;
