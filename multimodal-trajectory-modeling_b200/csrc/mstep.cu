@@ -432,7 +432,7 @@ __device__ __forceinline__ int regress_from_moments(const RD &rd, const double *
 }
 
 template <int D_, int L_>
-__global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0, int stage) {
+__global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0) {
     const int r = blockIdx.x;  // batched restarts: one block per fit
     FinalizeArgs a = a0;
     Ctrl *ctrl = a0.ctrl + r;
@@ -443,16 +443,6 @@ __global__ void finalize_kernel(const FinalizeArgs a0, const double *tail0, int 
     a.stats = a0.stats + (size_t)r * ((size_t)n_c * sstride + (tail0 ? kTail : 0));
     a.params = a0.params + (size_t)r * n_c * pstride;
     a.switch_hist = a0.switch_hist ? a0.switch_hist + (size_t)r * a.n_steps : nullptr;
-    // The (all-reduced) statistics go through shared memory first: the solves below read ~100 values per thread one
-    // after the other, each a dependent global-memory latency (31 us per launch before, on the critical path of every
-    // EM iteration); one cooperative coalesced copy instead.
-    extern __shared__ double s_st[];
-    if (stage) {
-        const int n_in = n_c * sstride + (tail0 ? kTail : 0);
-        for (int k = threadIdx.x; k < n_in; k += blockDim.x) s_st[k] = a.stats[k];
-        __syncthreads();
-        a.stats = s_st;
-    }
     const double *tail = tail0 ? a.stats + (size_t)n_c * sstride : nullptr;
     __shared__ int s_go;
     __shared__ int s_status;
@@ -798,21 +788,15 @@ cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, do
 }
 
 cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStream_t s) {
+    // (28 us per launch on the critical path of every iteration: serial Cholesky / division chains of 3 n_c threads.
+    // Staging the statistics in shared memory first was measured and changed nothing: it is not load latency.)
     const int blocks = a.R > 1 ? a.R : 1;
-    int threads = 128;
+    int threads = 32;
     while (threads < 3 * a.n_c && threads < 256) threads *= 2;
-    const size_t bytes = ((size_t)a.n_c * stats_stride(a.d, a.l) + kTail) * sizeof(double);
-    const int stage = bytes <= 160 * 1024 ? 1 : 0;
-    const size_t smem = stage ? bytes : 0;
-#define MTM_CASE(DD, LL)                                                                                            \
-    if (a.d == DD && a.l == LL) {                                                                                   \
-        if (smem > 48 * 1024) {                                                                                     \
-            cudaError_t e = cudaFuncSetAttribute(finalize_kernel<DD, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 (int)smem);                                                        \
-            if (e != cudaSuccess) return e;                                                                         \
-        }                                                                                                           \
-        finalize_kernel<DD, LL><<<blocks, threads, smem, s>>>(a, tail, stage);                                      \
-        return cudaGetLastError();                                                                                  \
+#define MTM_CASE(DD, LL)                                             \
+    if (a.d == DD && a.l == LL) {                                    \
+        finalize_kernel<DD, LL><<<blocks, threads, 0, s>>>(a, tail); \
+        return cudaGetLastError();                                   \
     }
     MTM_CASE(4, 4)
     MTM_CASE(2, 4)
@@ -822,11 +806,7 @@ cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStrea
     MTM_CASE(2, 2)
     MTM_CASE(5, 3)
 #undef MTM_CASE
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(finalize_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    finalize_kernel<0, 0><<<blocks, threads, smem, s>>>(a, tail, stage);
+    finalize_kernel<0, 0><<<blocks, threads, 0, s>>>(a, tail);
     return cudaGetLastError();
 }
 
