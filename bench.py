@@ -667,24 +667,31 @@ def leg_e2e(ctx, cfg, run, z, x, steps):
     lo_hi = ctx.max_over_ranks([gbs, -gbs])
     out["h2d_probe"] = {"gbs_per_rank_max": lo_hi[0], "gbs_per_rank_min": -lo_hi[1],
                         "note": "one cudaMemcpyAsync of the pinned shard per array, all ranks concurrently"}
-    # per fit: upload once (pinned -> HBM), pattern order, W+1.. resident iterations, labels back
+    # per fit: upload once (pinned -> HBM), pattern order, k_fit resident iterations, labels back.  Run twice, report
+    # the second: the first pays the caching allocator's cudaMallocs of two more 2.5-GB copies (hundreds of ms, varying)
     k_fit = 5
-    ctx.barrier()
-    t0, t1, t2 = ctx.event(), ctx.event(), ctx.event()
-    t0.record()
-    dd = ctx.mtm.DeviceData(zh, xh, ctx.device, pattern_order=True)
-    aa = dd.to_resident(a_caller)
-    t1.record()
-    _, info = ctx.eng.em_fit(dd, aa, n_c, 0.0, k_fit)
-    lab = dd.from_resident(aa).to("cpu", non_blocking=False)
-    t2.record()
-    ctx.barrier()
-    ms_fit, ms_up = ctx.max_over_ranks([t0.elapsed_time(t2), t0.elapsed_time(t1)])
-    out["per_fit"] = {"ms_total": ms_fit, "ms_upload_and_order": ms_up, "em_iterations": int(info["n_e_steps"]),
+    for attempt in range(2):
+        ctx.barrier()
+        t0, t1, t2 = ctx.event(), ctx.event(), ctx.event()
+        t0.record()
+        dd = ctx.mtm.DeviceData(zh, xh, ctx.device, pattern_order=True)
+        aa = dd.to_resident(a_caller)
+        t1.record()
+        _, info = ctx.eng.em_fit(dd, aa, n_c, 0.0, k_fit)
+        lab = dd.from_resident(aa).to("cpu", non_blocking=False)
+        t2.record()
+        ctx.barrier()
+        ms_fit, ms_up = ctx.max_over_ranks([t0.elapsed_time(t2), t0.elapsed_time(t1)])
+        if attempt == 0:
+            first_ms = ms_fit
+            ctx.eng.bind(run.data)
+            del dd, aa
+    out["per_fit"] = {"ms_total": ms_fit, "ms_upload_and_order": ms_up, "ms_total_first_call": first_ms,
+                      "em_iterations": int(info["n_e_steps"]),
                       "exit": info["exit"], "value": n_total * n_c * max(1, int(info["n_e_steps"])) / (ms_fit * 1e-3),
                       "unit": UNIT, "labels_downloaded": int(lab.numel()),
-                      "note": "DeviceData(pinned host z, x) + mtm_em_fit + labels back: the data cross PCIe once per "
-                              "fit, as in train()"}
+                      "note": "DeviceData(pinned host z, x) + mtm_em_fit + labels back: the data cross PCIe once per fit, as in "
+                              "train(); second of two identical calls (the first also pays the allocator's cudaMallocs)"}
     ctx.eng.bind(run.data)
     del zh, xh, dd, aa
     return out

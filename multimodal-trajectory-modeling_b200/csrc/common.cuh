@@ -8,8 +8,11 @@
 
 namespace mtm {
 
-constexpr int kEThreads = 128;  // E-step: one thread per trajectory, 4 warps per block
-constexpr int kSThreads = 128;  // statistics: one thread per trajectory, tile = block
+#ifndef MTM_E_THREADS
+#define MTM_E_THREADS 128  // tuning knob of tools/build_variant.sh (64 and 96 measured slower, profiles/r2_experiments.md)
+#endif
+constexpr int kEThreads = MTM_E_THREADS;  // E-step: one thread per trajectory, 4 warps per block
+constexpr int kSThreads = MTM_E_THREADS;  // statistics: one thread per trajectory, tile = block
 
 // Device-resident control block of the EM loop: written by the kernels, polled by the host.
 struct Ctrl {

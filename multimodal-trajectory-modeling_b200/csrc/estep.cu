@@ -262,7 +262,7 @@ int estep_grid(int64_t n, int sm_count, bool fused) {
     // pattern-ordered set 12 / 18 / 24 / 36 / 48 / 72 blocks per SM give 18.53 / 18.35 / 18.19 / 18.09 / 18.10 /
     // 18.08 ms (first build: 3 / 6 / 12 / 24 / 64 -> 23.8 / 23.0 / 22.4 / 22.1 / 22.0, profiles/r1h_grid_sweep.txt).
     // 36 per SM (72 MB of partials at n_c = 8).
-    int per_sm = fused ? 36 : 32;
+    int per_sm = (fused ? 36 : 32) * 128 / kEThreads;
     if (const char *e = getenv(fused ? "MTM_FUSED_BLOCKS_PER_SM" : "MTM_ESTEP_BLOCKS_PER_SM")) {  // tuning knob
         const int v = atoi(e);
         if (v > 0) per_sm = v;
