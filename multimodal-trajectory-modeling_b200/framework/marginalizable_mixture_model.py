@@ -638,22 +638,10 @@ class MMLinGaussSS_marginalizable:
                                           return_objectives: bool = False, use_cache: bool = True):
         """k-means start (seed 0) + n_starts random starts (seeds 100+i); best by strict > on Q
         (MMM:1368-1471).  The training set is uploaded once and shared by all restarts."""
-        if bool(use_cache):
-            try:
-                pfile = sorted(glob.glob(os.path.join(home_dir, "tmp", f"mmm-{self.hex_hash}*")),
-                               key=os.path.getmtime).pop()
-                best_mdl = MMLinGaussSS_marginalizable.from_pickle(
-                    pfile, training_data={"states": self.states, "observations": self.observations})
-                assert self.hex_hash == best_mdl.hex_hash
-                if verbose:
-                    print(f"Loaded model {best_mdl.last_trained=} from cache.")
-                return best_mdl
-            except IndexError:
-                if verbose:
-                    print("No model found in cache.")
-            except Exception as err:  # noqa: BLE001 - mirrors the reference
-                if verbose:
-                    print(f"Issue loading cached model -- encountered {err}")
+        if use_cache:
+            cached = self._cached_model(verbose)
+            if cached is not None:
+                return cached
 
         shared = self._train_data()
         best_mdl = MMLinGaussSS_marginalizable(n_clusters=self.n_clusters, states=self.states,
@@ -687,6 +675,29 @@ class MMLinGaussSS_marginalizable:
         if return_objectives:
             return best_mdl, np.array(objective_list)
         return best_mdl
+
+    def _cached_model(self, verbose: bool = False):
+        """The newest model cached for this data / n_clusters / alpha under ``<home>/tmp`` (file names
+        ``mmm-<hex_hash>-<UTC stamp>.p.gz``, MMM:227-245), or None.  A file that cannot be loaded, or whose stored key
+        differs, counts as a miss (MMM:1400-1428)."""
+        hits = glob.glob(os.path.join(home_dir, "tmp", f"mmm-{self.hex_hash}*"))
+        if not hits:
+            if verbose:
+                print("No model found in cache.")
+            return None
+        newest = max(hits, key=os.path.getmtime)
+        try:
+            mdl = MMLinGaussSS_marginalizable.from_pickle(
+                newest, training_data={"states": self.states, "observations": self.observations})
+            if mdl.hex_hash != self.hex_hash:
+                raise ValueError("cache key mismatch")
+        except Exception as err:  # noqa: BLE001
+            if verbose:
+                print(f"Issue loading cached model -- encountered {err}")
+            return None
+        if verbose:
+            print(f"Loaded model {mdl.last_trained=} from cache.")
+        return mdl
 
     def _batched_random_restarts(self, shared, n_starts, n_steps):
         """[(status, Q, factory)] for seeds 100 .. 100+n_starts-1 (MMM:1449-1455), fitted together."""

@@ -409,6 +409,22 @@ def test_pickle_roundtrip(mix, tmp_path):
     assert back.hex_hash == mdl.hex_hash
     assert np.array_equal(back._packed_params(), mdl._packed_params())
     assert np.array_equal(back.mle_cluster_assignment(), mdl.mle_cluster_assignment())
+    # the cache of train_with_multiple_random_starts (MMM:1400-1428, 1467-1468): the second call is a cache hit
+    import mtm_b200.framework.marginalizable_mixture_model as mod
+
+    old_home = mod.home_dir
+    mod.home_dir = str(tmp_path / "home")
+    try:
+        proto = mix.MMLinGaussSS_marginalizable(n_clusters=2, states=z, observations=x)
+        first = proto.train_with_multiple_random_starts(n_starts=3, n_steps=20, use_cache=True)
+        assert len(list((tmp_path / "home" / "tmp").glob(f"mmm-{proto.hex_hash}*"))) == 1
+        again = mix.MMLinGaussSS_marginalizable(n_clusters=2, states=z, observations=x).train_with_multiple_random_starts(
+            n_starts=3, n_steps=20, use_cache=True)
+        assert again is not first and again.last_trained == first.last_trained
+        assert np.array_equal(again._packed_params(), first._packed_params())
+        assert np.array_equal(again.cluster_assignment, first.cluster_assignment)
+    finally:
+        mod.home_dir = old_home
 
 
 def test_kmeans_start_on_device(g_restarts, mix, eng, monkeypatch):
