@@ -123,7 +123,15 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     unsigned int sw_acc = 0;
     int bad = 0;
 
+#ifdef MTM_STATS_TIMING
+    long long t_e = 0, t_all0 = clock64();
+    int n_my_tiles = 0;
+#endif
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#ifdef MTM_STATS_TIMING
+        const long long t_tile0 = clock64();
+        ++n_my_tiles;
+#endif
         const int64_t i_raw = tile * kEThreads + tid;
         const bool valid = i_raw < n;
         const int64_t i = valid ? i_raw : n - 1;  // clamp: the tail lanes compute and discard
@@ -178,8 +186,18 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
                 if ((tid & 31) == 0 && m) atomicAdd(&s_cnt[c], (unsigned int)__popc(m));
             }
         }
+#ifdef MTM_STATS_TIMING
+        t_e += clock64() - t_tile0;
+#endif
         if (FUSE) stats_tile(dm, a.z, a.x, a.ld, a.T, i, valid ? arg : -1, a.n_c, stats_base, a.pivot);
     }
+#ifdef MTM_STATS_TIMING
+    if (FUSE && blockIdx.x == 0 && tid == 0 && n_my_tiles > 4)
+        printf("block 0: %d tiles, cycles per tile: E+argmax %lld | sort %lld pass1 %lld red1 %lld red2 %lld pass2 %lld red3 %lld | total %lld\n",
+               n_my_tiles, t_e / n_my_tiles, g_stats_cyc[0] / n_my_tiles, g_stats_cyc[1] / n_my_tiles, g_stats_cyc[2] / n_my_tiles,
+               g_stats_cyc[3] / n_my_tiles, g_stats_cyc[4] / n_my_tiles, g_stats_cyc[5] / n_my_tiles,
+               (clock64() - t_all0) / n_my_tiles);
+#endif
 
     // block epilogue: integer counters by atomics (exact, order-free), fp64 sums in a fixed order
     if (bad) atomicOr(&ctrl->status, bad);

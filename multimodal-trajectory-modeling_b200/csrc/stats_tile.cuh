@@ -132,6 +132,17 @@ __device__ __forceinline__ void centre_row(double (&v)[NM], int n, const double 
 // PREFETCH (stand-alone statistics kernel only): the rows come from HBM and every load below is consumed where it
 // is issued — ask for all 2T rows of the trajectory up front.  In the fused E-step the rows are in L2 / L1 already
 // (the same prefetches there measured 0.2 % slower) and its code must not change shape, so it is a template flag.
+#ifdef MTM_STATS_TIMING  // diagnostic variant (tools/build_variant.sh): cycles per phase of block 0, printed by estep.cu
+__device__ long long g_stats_cyc[8];
+#define MTM_TICK(k)                                                                \
+    do {                                                                           \
+        const long long _now = clock64();                                          \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_stats_cyc[k] += _now - _tick;   \
+        _tick = _now;                                                              \
+    } while (0)
+#else
+#define MTM_TICK(k)
+#endif
 template <class DM, bool PREFETCH = false>
 __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restrict__ z, const double *__restrict__ x,
                                            int64_t ld, int T, int64_t i, int label, int n_c, unsigned char *smem_base,
@@ -153,6 +164,9 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
     double *s_acc = sm.acc, *s_feat = sm.feat;
     int *s_start = sm.start, *s_wcnt = sm.wcnt;
     if (label < 0 || label >= n_c) label = -1;
+#ifdef MTM_STATS_TIMING
+    long long _tick = clock64();
+#endif
 
     // ---- stable counting sort of the tile's labels -> member lists ----
     int my_rank = 0;
@@ -183,6 +197,7 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
         dd_add(acc[0], acc[1], (double)(s_start[c + 1] - s_start[c]));
     }
 
+    MTM_TICK(0);  // sort
     const double *z_i = z + i * d;
     const double *x_i = x + i * l;
     if (PREFETCH) {
@@ -223,8 +238,11 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
             for (int k = 0; k < DMX; ++k) zc[k] = zn[k];
             okc = okn;
         }
+        MTM_TICK(1);  // pass 1
         reduce_by_cluster<F1M>(f1, F1, s_feat, pos, s_start, n_c, s_acc, sstride, 1);
+        MTM_TICK(2);
         reduce_by_cluster<F2M>(f2, F2, s_feat, pos, s_start, n_c, s_acc, sstride, 1 + F1);
+        MTM_TICK(3);
     }
     // ---- pass 2: measurement moments ----
     {
@@ -258,7 +276,9 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
                 add_moments<K3>(f3, w, d + l, ok && label >= 0);
             }
         }
+        MTM_TICK(4);  // pass 2
         reduce_by_cluster<F3M>(f3, F3, s_feat, pos, s_start, n_c, s_acc, sstride, 1 + F1 + F2);
+        MTM_TICK(5);
     }
 }
 
