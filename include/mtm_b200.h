@@ -308,8 +308,13 @@ int mtm_kmeans_init(mtm_handle *h, const mtm_data *data, const int64_t *perm_dev
  *   e.g. z (T, n, d): rows = T, w = d;  labels (n): rows = 1;  ll / probs (n_c, n): rows = n_c, w = 1.
  *   Out of place only.  Enqueued on the handle's stream.
  * Every other entry point is order-agnostic: it works on whatever order the bound data and the label
- * array share. */
+ * array share.
+ * mtm_pattern_order and mtm_kmeans_init work in a grow-only workspace owned by the handle (about 10 bytes per
+ * trajectory for the order, 2 (n, d) copies for k-means): allocating and freeing it per call cost tens to hundreds
+ * of milliseconds once peer GPUs have the device mapped.  mtm_release_workspace gives it back (synchronises);
+ * mtm_destroy does too. */
 int mtm_pattern_order(mtm_handle *h, const mtm_data *data, int64_t *perm_dev);
+int mtm_release_workspace(mtm_handle *h);
 int mtm_permute_f64(mtm_handle *h, const double *src_dev, double *dst_dev, int64_t rows, int64_t n, int w,
                     const int64_t *perm_dev, int inverse);
 int mtm_permute_i32(mtm_handle *h, const int32_t *src_dev, int32_t *dst_dev, int64_t rows, int64_t n,

@@ -111,6 +111,10 @@ struct mtm_handle {
     size_t nanmean_cap = 0;
     long long *d_rng = nullptr;  // mtm_random_labels: rejection list [kRngCap] + counter, allocated on first use
     long long *h_rng = nullptr;  // pinned mirror
+    // grow-only workspace of mtm_pattern_order / mtm_kmeans_init (cudaMalloc + cudaFree per call cost tens to
+    // hundreds of ms once peers have the device mapped); mtm_release_workspace or mtm_destroy frees it
+    unsigned char *d_work = nullptr;
+    size_t work_cap = 0;
     std::string err;
     int64_t launches = 0;
 };
@@ -482,6 +486,7 @@ int mtm_destroy(mtm_handle *h) {
     cudaFree(h->p2p_counter);
     cudaFree(h->d_rng);
     cudaFreeHost(h->h_rng);
+    cudaFree(h->d_work);
     cudaFree(h->d_pivot);
     cudaFree(h->d_nanmean);
     cudaFree(h->d_ctrl);
@@ -1198,16 +1203,22 @@ int mtm_pattern_order(mtm_handle *h, const mtm_data *data, int64_t *perm_dev) {
     if (!data->z_dev) return fail(h, -1, "mtm_pattern_order needs hidden states (z_dev)");
     if (data->n < 1 || data->T < 1 || data->d < 1 || data->d > MTM_MAX_DIM) return fail(h, -1, "bad data shape");
     DeviceGuard g(h->device);
-    void *scratch = nullptr;
-    MTM_CUDA(h, cudaMalloc(&scratch, order_scratch_bytes(data->n, h->sm_count)));
-    struct Free {  // scratch is released on every exit path
-        void *p;
-        ~Free() { cudaFree(p); }
-    } free_scratch{scratch};
+    if (int rc = ensure(h, h->d_work, h->work_cap, order_scratch_bytes(data->n, h->sm_count))) return rc;
+    void *scratch = h->d_work;
     MTM_CUDA(h, launch_pattern_order(data->z_dev, data->n, data->ld > 0 ? data->ld : data->n, data->T, data->d,
                                      h->sm_count, scratch, perm_dev, h->stream));
     h->launches += (data->T > 4) ? 7 : 4;
-    MTM_CUDA(h, cudaStreamSynchronize(h->stream));  // the scratch is freed on return
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));  // the workspace may be reused from another stream next
+    return 0;
+}
+
+int mtm_release_workspace(mtm_handle *h) {
+    if (!h) return -1;
+    DeviceGuard g(h->device);
+    MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->d_work) MTM_CUDA(h, cudaFree(h->d_work));
+    h->d_work = nullptr;
+    h->work_cap = 0;
     return 0;
 }
 
@@ -1250,12 +1261,8 @@ int mtm_kmeans_init(mtm_handle *h, const mtm_data *data, const int64_t *perm_dev
     const int w = data->d;
     const size_t rows_d = (size_t)n * w;
     const size_t total = 2 * rows_d + kmeans_scratch_doubles(n, w, n_c, h->sm_count) + (size_t)n_c * w + (n + 1) / 2 + 8;
-    double *buf = nullptr;
-    MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&buf), total * sizeof(double)));
-    struct Free {  // scratch is released on every exit path
-        void *p;
-        ~Free() { cudaFree(p); }
-    } free_buf{buf};
+    if (int rc = ensure(h, h->d_work, h->work_cap, total * sizeof(double))) return rc;
+    double *buf = reinterpret_cast<double *>(h->d_work);
     double *rows_res = buf, *rows = buf + rows_d, *centers = rows + rows_d, *scratch = centers + (size_t)n_c * w;
     int32_t *labels = reinterpret_cast<int32_t *>(scratch + kmeans_scratch_doubles(n, w, n_c, h->sm_count));
     MTM_CUDA(h, launch_first_rows(data->z_dev, n, data->ld > 0 ? data->ld : n, data->T, w, rows_res, h->sm_count, h->stream));

@@ -390,6 +390,10 @@ class Engine:
         self._chk(self.lib.mtm_fingerprint(self.h, ctypes.byref(st), perm, key))
         return f"{key[0]:016x}{key[1]:016x}"
 
+    def release_workspace(self):
+        """Give back the grow-only workspace of pattern_order / kmeans_init (mtm_release_workspace)."""
+        self._chk(self.lib.mtm_release_workspace(self.h))
+
     def fp64_peak(self, reps=10):
         self._sync_stream()
         out = ctypes.c_double(0.0)
