@@ -749,6 +749,11 @@ def leg_c5(ctx, cfg, run, z, x, n_restarts, ncs, n_steps=2):
     n_loc = hi - lo
     ds = data_stats(torch, z, x)
     sets, ms_sum, per_nc, exits = 0, 0.0, {}, {}
+    # untimed: one iteration at the largest n_c sizes the library's scratch and the caching allocator's blocks once
+    # (a cudaFree + cudaMalloc of a grown buffer inside a timed call costs 50-250 ms with peers mapped)
+    a = run.data.to_resident(labels_global(n_total, lo, hi, max(ncs), ctx.device, seed=7, rows=n_restarts))
+    ctx.eng.sweep_fit(run.data, a, max(ncs), 0.0, 1, want_scores=False)
+    del a
     with ClockSampler(ctx.local_rank) as clk:
         for n_c in ncs:
             a = labels_global(n_total, lo, hi, n_c, ctx.device, seed=100_000 * n_c, rows=n_restarts)

@@ -671,6 +671,23 @@ def test_pattern_order(eng):
         assert np.array_equal(ordered.from_resident(r1["assign"]).cpu().numpy(), r0["assign"].cpu().numpy())
 
 
+def test_pattern_order_workspace(eng):
+    """The order works in the handle's grow-only workspace: the same permutation from a fresh, a reused (larger set
+    first, then a smaller one) and a released workspace."""
+    import mtm_b200
+
+    perms = []
+    for n in (40_000, 3_001, 40_000):
+        z, x = _synthetic(n, 8, 4, 4, 3, seed=5)
+        perms.append(mtm_b200.DeviceData(z, x, eng.device, pattern_order=True).perm.cpu().numpy())
+        if n < 10_000:
+            eng.release_workspace()
+    assert np.array_equal(perms[0], perms[2])
+    assert np.array_equal(np.sort(perms[1]), np.arange(3_001))
+    eng.release_workspace()
+    eng.release_workspace()  # idempotent
+
+
 def test_pattern_order_fit_equals_plain_fit(eng):
     """A whole fit on the pattern-ordered set: same labels and switch history as in the caller's order (the
     statistics are summed in another order, so parameters agree to rounding, not bit for bit)."""
