@@ -504,10 +504,11 @@ class EmRunner:
         st = ctx.sum_over_ranks(torch.tensor([float(info.status)], dtype=torch.float64, device=ctx.device))
         ok = min(sizes) > 3 and int(st.item()) == 0 and sum(sizes) == n_total
         return {"ok": bool(ok), "min_count": min(sizes), "min_count_library": int(info.min_count),
-                "status": int(info.status), "cluster_sizes": sizes, "n_switches": int(sw.item())}
+                "status": int(info.status), "cluster_sizes": sizes, "n_switches": int(sw.item()),
+                "stats_mode": int(info.stats_mode)}
 
 
-def em_roofline(ctx, cfg, ds, n_loc, ms_e, ms_m, pattern_order, kernel, wsc):
+def em_roofline(ctx, cfg, ds, n_loc, ms_e, ms_m, pattern_order, kernel, wsc, delta=False):
     T, d, l, n_c = cfg["T"], cfg["d"], cfg["l"], cfg["n_c"]
     f_eval = flops_per_eval(T, d, l, ds["kz"], ds["kx"])
     f_survey = flops_per_eval_survey(T, d, l, ds["kz"] + ds["kx"])
@@ -518,7 +519,7 @@ def em_roofline(ctx, cfg, ds, n_loc, ms_e, ms_m, pattern_order, kernel, wsc):
     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of THIS launch configuration
     # (profiles/r2i_fused_ncu_summary.md: 5.168793 GB read = one pass over the data + labels, 112.1 MB written = new
     # labels + 72 MB of block partials); any other size has no capture
-    captured = (n_loc == 10_000_000 and (T, d, l, n_c) == (8, 4, 4, 8) and pattern_order)
+    captured = (n_loc == 10_000_000 and (T, d, l, n_c) == (8, 4, 4, 8) and pattern_order and not delta)
     return {"bound": "fp64", "achieved": tf, "peak": ctx.fp64_peak, "unit": "TFLOP/s", "frac": tf / ctx.fp64_peak,
             "traffic": (5.168793e9 + 112.147968e6) if captured else None,
             "traffic_unit": "bytes per launch (ncu capture of this configuration)" if captured else None,
@@ -572,14 +573,35 @@ def leg_em(ctx, cfg, steps, warmup, tag, pattern_order=True):
     launches = ctx.eng.launch_count() - launches0
     ms_step = ms_total / steps
     chk = run.check(n_total)
+    # how the M-step statistics of the timed iteration were formed (mtm_b200.h, "delta statistics": late iterations
+    # move few trajectories and only those are visited), and the same iteration with the mode switched off
+    k_full = max(1, min(steps, 5))
+    ctx.eng.set_delta_stats(False)
+    run.restore()
+    run.phase(3)
+    full_total, full_e, _ = run.timed_steps(k_full)
+    chk_full = run.check(n_total)
+    params_full = run.params.clone()
+    ctx.eng.set_delta_stats(True)
+    run.check(n_total)  # leaves the runner in the state after the timed iteration, formed the default way
+    statistics = {"mode_of_timed_iteration": "delta" if chk["stats_mode"] == 1 else "full",
+                  "switch_fraction": chk["n_switches"] / n_total,
+                  "ms_per_step_full_statistics": full_total / k_full, "kernel_ms_full_statistics": full_e,
+                  "steps_full_statistics": k_full, "mode_when_switched_off": chk_full["stats_mode"],
+                  "params_max_rel_err_delta_vs_full": rel_err(run.params.cpu().numpy(), params_full.cpu().numpy()),
+                  "note": "value / ms_per_step are the iteration as mtm_em_step and mtm_em_fit run it (delta statistics "
+                          "when the previous iteration moved at most n/8 labels); the *_full_statistics fields time the "
+                          "same iteration with every cluster re-summed from all members, as the reference's M_step does"}
     out = {"tag": tag, "n_total": n_total, "n_per_gpu": n_loc, "n_c": n_c, "steps": steps, "ms_per_step": ms_step,
            "value": n_total * n_c / (ms_step * 1e-3), "em_iters_per_s": 1e3 / ms_step, "clocks": clk.summary(),
-           "gpu_launches": int(launches), "workload_check": chk, "order_ms": run.order_ms,
+           "gpu_launches": int(launches), "workload_check": chk, "statistics": statistics, "order_ms": run.order_ms,
            "present_scalars_per_trajectory": {"z": ds["kz"], "x": ds["kx"]}, "warp_step_paths": wsc,
            "roofline": em_roofline(ctx, cfg, ds, n_loc, ms_e, ms_m, pattern_order,
-                                   "estep_kernel<4,4,HAS_Z=1,CONSTP=1> with the M-step statistics fused in (the "
-                                   "timed span also holds the two ~10 us reduction kernels and, for N > 1, the "
-                                   "all-reduce)", wsc)}
+                                   ("estep_delta_kernel<4,4,CONSTP=1>: E-step + delta statistics of the movers"
+                                    if chk["stats_mode"] == 1 else
+                                    "estep_kernel<4,4,HAS_Z=1,CONSTP=1> with the M-step statistics fused in") +
+                                   " (the timed span also holds the two label-hash passes, the two ~10 us reduction "
+                                   "kernels and, for N > 1, the all-reduce)", wsc, delta=chk["stats_mode"] == 1)}
     # state after the timed iteration: labels in the caller's order, gathered; Q and LL all-reduced by the library
     labels = ctx.gather_labels(run.data.from_resident(run.assign), n_total)
     q, ll, st = ctx.eng.score(run.data, run.params, n_c)
@@ -976,7 +998,7 @@ def main():
                 "em_iters_per_s": main_leg["em_iters_per_s"],
                 "clocks": main_leg["clocks"], "e2e": e2e, "gpu_launches": main_leg["gpu_launches"],
                 "roofline": main_leg["roofline"], "cpu_baseline": cpu_base, "parity": parity,
-                "workload_check": chk, "state": main_leg["state"],
+                "workload_check": chk, "statistics": main_leg["statistics"], "state": main_leg["state"],
                 "present_scalars_per_trajectory": main_leg["present_scalars_per_trajectory"],
                 "warp_step_paths": main_leg["warp_step_paths"], "configs": configs}
         bad = []

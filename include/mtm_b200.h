@@ -84,7 +84,8 @@ typedef struct {
                             and the call all-reduces; mtm_estep itself is local) */
     int64_t min_count;   /* smallest cluster size after the E-step (local) */
     int32_t status;      /* MTM_STATUS_* bits */
-    int32_t reserved;
+    int32_t stats_mode;  /* mtm_em_step: how the M-step statistics of this iteration were formed: 0 = summed over
+                            all trajectories, 1 = delta statistics (see mtm_set_delta_stats); 0 elsewhere */
 } mtm_estep_info;
 
 typedef struct {
@@ -167,7 +168,21 @@ int mtm_mstep(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, d
  * params_dev (new labels into assign_dev, switch count), then M-step of the new labels into params_dev.
  * The statistics are accumulated inside the E-step kernel (one pass over the data).  phases: bit 0 = the
  * E-step + statistics + reduction (+ all-reduce) part, bit 1 = the parameter solve; 3 = both (the split
- * only exists so that a benchmark can time the dominant kernel on its own).  Synchronises if info != NULL. */
+ * only exists so that a benchmark can time the dominant kernel on its own).  Synchronises if info != NULL.
+ *
+ * Delta statistics (mtm_em_step and the iterations of mtm_em_fit; single fits with hidden states).  The reference
+ * recomputes every cluster's sums from all of its members in every M-step (MMM:1254-1308).  Late EM iterations move
+ * few trajectories, and the sums of the new labels are those of the old labels plus / minus the moments of the movers.
+ * The handle keeps, on the device, the reduced sums (as double-double pairs) of the last two label vectors its fused
+ * E-step produced, keyed by a 128-bit hash of the labels.  An iteration whose starting labels hash to a cached entry
+ * whose own iteration changed at most n/8 labels only visits the trajectories that change cluster; otherwise it
+ * sums everything and refills the cache.  The decision is taken on the device, per rank, without a host round
+ * trip; labels changed by the caller simply miss the cache.  A mover's moments are formed by the same operations
+ * as in the full pass, so the two modes differ only in the order trajectories are added (as grids and GPU counts
+ * do): same labels, parameters equal to rounding.  The cache is dropped by every mtm_set_data (re-bind after
+ * changing the resident buffers in place), by a new pivot and at the start of mtm_em_fit.
+ * mtm_set_delta_stats(h, 0) turns the mode off (every iteration sums everything); default on. */
+int mtm_set_delta_stats(mtm_handle *h, int enable);
 int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, double *params_dev, int phases,
                 mtm_estep_info *info);
 

@@ -39,7 +39,7 @@ class MtmData(ctypes.Structure):
 
 class EStepInfo(ctypes.Structure):
     _fields_ = [("n_switches", ctypes.c_int64), ("min_count", ctypes.c_int64), ("status", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("stats_mode", ctypes.c_int32)]
 
 
 class KMeansInfo(ctypes.Structure):
@@ -86,6 +86,7 @@ SIGNATURES = {
     "mtm_random_labels": (_i, [_vp, ctypes.POINTER(ctypes.c_uint64), _i, _i64, _vp, ctypes.POINTER(_i)]),
     "mtm_pattern_order": (_i, [_vp, ctypes.POINTER(MtmData), _vp]),
     "mtm_release_workspace": (_i, [_vp]),
+    "mtm_set_delta_stats": (_i, [_vp, _i]),
     "mtm_permute_f64": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _vp, _i]),
     "mtm_permute_i32": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i]),
     "mtm_kmeans_init": (_i, [_vp, ctypes.POINTER(MtmData), _vp, _i, _i64, ctypes.POINTER(_d), _i, _i, _d, _vp,

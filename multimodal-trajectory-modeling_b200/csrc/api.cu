@@ -115,6 +115,11 @@ struct mtm_handle {
     // hundreds of ms once peers have the device mapped); mtm_release_workspace or mtm_destroy frees it
     unsigned char *d_work = nullptr;
     size_t work_cap = 0;
+    // delta statistics (common.cuh StatsCache): device-side cache of the reduced sums of the last two label vectors
+    StatsCache *d_cache = nullptr;
+    double *d_bases = nullptr;  // 2 entries x n_vals x (hi, lo)
+    size_t bases_cap = 0;
+    bool delta_enabled = true;
     std::string err;
     int64_t launches = 0;
 };
@@ -196,7 +201,8 @@ bool can_fuse(const mtm_data *dt, int n_c) {
 
 int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n_c, int T0, int32_t *assign,
                   int count_switches, double *ll, double *probs, double *prenorm, unsigned long long *counts,
-                  double *score_partials, int check_done, int *grid_out, bool fused = false, int R = 1) {
+                  double *score_partials, int check_done, int *grid_out, bool fused = false, int R = 1,
+                  const StatsCache *cache = nullptr) {
     EStepArgs a{};
     a.z = dt->z_dev;
     a.x = dt->x_dev;
@@ -226,6 +232,7 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
         if (int rc = ensure(h, h->d_partials, h->partials_cap, 2 * n_vals * ((size_t)grid + kReduceSlices) * R)) return rc;
         a.stats_partials = h->d_partials;
         memcpy(a.pivot, h->pivot, sizeof(a.pivot));  // valid: the callers of the fused mode ran ensure_pivot
+        a.cache = (R == 1) ? cache : nullptr;
     }
     const size_t smem = estep_smem(n_c, a.T0, a.d, a.l, fused);
     if (smem > 200 * 1024) return fail(h, -1, "E-step shared memory %zu B too large (n_c * T0 too big)", smem);
@@ -247,8 +254,34 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
         if (a.score_partials) b.score_partials = a.score_partials + 2 * (size_t)r0 * grid;
         if (a.stats_partials) b.stats_partials = a.stats_partials + (size_t)r0 * grid * nv2;
         MTM_CUDA(h, launch_estep(b, grid, smem, h->stream));
-        h->launches += 1;
+        h->launches += b.cache ? 2 : 1;  // with the cache: estep_kernel and its delta twin, one of which returns at once
     }
+    return 0;
+}
+
+// forget the cached statistics (new data, new pivot, resized buffers); stream ordered
+int invalidate_stats_cache(mtm_handle *h) {
+    if (h->d_cache) MTM_CUDA(h, cudaMemsetAsync(h->d_cache, 0, sizeof(StatsCache), h->stream));
+    return 0;
+}
+
+// the cache of a single fit's fused iterations, or nullptr when delta statistics cannot be used for this shape
+int stats_cache_for(mtm_handle *h, int n_c, StatsCache **out) {
+    *out = nullptr;
+    const mtm_data &dt = h->data;
+    if (stats_delta_smem_bytes(n_c, dt.d, dt.l) > estep_smem(n_c, dt.T, dt.d, dt.l, true) - estep_smem(n_c, dt.T, dt.d, dt.l, false))
+        return 0;  // the per-warp accumulators do not fit the fused kernel's statistics region
+    if (!h->d_cache) {
+        MTM_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->d_cache), sizeof(StatsCache)));
+        MTM_CUDA(h, cudaMemsetAsync(h->d_cache, 0, sizeof(StatsCache), h->stream));
+    }
+    const size_t need = 4 * (size_t)n_c * stats_stride(dt.d, dt.l);
+    if (need > h->bases_cap) {
+        MTM_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (int rc = ensure(h, h->d_bases, h->bases_cap, need)) return rc;
+        if (int rc = invalidate_stats_cache(h)) return rc;
+    }
+    *out = h->d_cache;
     return 0;
 }
 
@@ -303,18 +336,19 @@ int ensure_pivot(mtm_handle *h) {
     }
     h->pivot_valid = true;
     h->pivot_world = world;
-    return 0;
+    return invalidate_stats_cache(h);  // cached sums were taken about the old pivot
 }
 
 // block partials in h->d_partials (from `grid` blocks) -> h->d_statsbuf [n_c*sstride | n_switches | n_local],
 // all-reduced over the communicator
-int enqueue_stats_reduce(mtm_handle *h, int n_c, int grid, int check_done, int with_switches, int R = 1) {
+int enqueue_stats_reduce(mtm_handle *h, int n_c, int grid, int check_done, int with_switches, int R = 1,
+                         const StatsCache *cache = nullptr) {
     const mtm_data &dt = h->data;
     const int n_vals = n_c * stats_stride(dt.d, dt.l);
     if (int rc = ensure(h, h->d_statsbuf, h->statsbuf_cap, ((size_t)n_vals + kTail) * R)) return rc;
     MTM_CUDA(h, launch_stats_reduce(h->d_partials, grid, n_vals, h->d_statsbuf,
                                     h->d_partials + 2 * (size_t)R * grid * n_vals, h->d_ctrl, check_done,
-                                    with_switches, (double)dt.n, R, h->stream));
+                                    with_switches, (double)dt.n, R, h->stream, cache, h->d_bases));
     h->launches += 2;
     return allreduce_stats(h, h->d_statsbuf, ((size_t)n_vals + kTail) * R, R);
 }
@@ -357,11 +391,25 @@ int enqueue_e_and_stats(mtm_handle *h, int n_c, const double *params, int32_t *a
     const mtm_data &dt = h->data;
     if (int rc = ensure_pivot(h)) return rc;
     if (can_fuse(&dt, n_c)) {
+        // single fit: the statistics cache decides on the device (label hash of the labels this E-step starts from)
+        // whether the iteration only visits the trajectories that change cluster
+        StatsCache *cache = nullptr;
+        if (R == 1)
+            if (int rc = stats_cache_for(h, n_c, &cache)) return rc;
+        if (cache) {
+            MTM_CUDA(h, launch_label_hash(assign, dt.n, n_c, cache, h->d_ctrl, check_done, 0, h->delta_enabled ? 1 : 0,
+                                          h->sm_count, h->stream));
+            h->launches += 1;
+        }
         int grid = 0;
         if (int rc = enqueue_estep(h, &dt, params, n_c, dt.T, assign, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                   check_done, &grid, true, R))
+                                   check_done, &grid, true, R, cache))
             return rc;
-        return enqueue_stats_reduce(h, n_c, grid, check_done, 1, R);
+        if (cache) {
+            MTM_CUDA(h, launch_label_hash(assign, dt.n, n_c, cache, h->d_ctrl, check_done, 1, 0, h->sm_count, h->stream));
+            h->launches += 1;
+        }
+        return enqueue_stats_reduce(h, n_c, grid, check_done, 1, R, cache);
     }
     if (int rc = enqueue_estep(h, &dt, params, n_c, dt.T, assign, 1, nullptr, nullptr, nullptr, nullptr, nullptr,
                                check_done, nullptr, false, R))
@@ -487,6 +535,8 @@ int mtm_destroy(mtm_handle *h) {
     cudaFree(h->d_rng);
     cudaFreeHost(h->h_rng);
     cudaFree(h->d_work);
+    cudaFree(h->d_cache);
+    cudaFree(h->d_bases);
     cudaFree(h->d_pivot);
     cudaFree(h->d_nanmean);
     cudaFree(h->d_ctrl);
@@ -525,7 +575,10 @@ int mtm_set_data(mtm_handle *h, const mtm_data *data) {
     if (!same) h->pivot_valid = false;
     h->data = *data;
     h->has_data = true;
-    return 0;
+    // cached statistics never survive a bind, not even of the same buffers: their contents may have changed, and a
+    // label vector that recurs (same seed, new data) must not find the old sums
+    DeviceGuard g(h->device);
+    return invalidate_stats_cache(h);
 }
 
 int mtm_estep(mtm_handle *h, const mtm_data *data, const double *params_dev, int n_c, int T0, int32_t *assign_dev,
@@ -549,7 +602,7 @@ int mtm_estep(mtm_handle *h, const mtm_data *data, const double *params_dev, int
         info->n_switches = (int64_t)h->h_ctrl->n_switches;
         info->min_count = (int64_t)mn;
         info->status = h->h_ctrl->status;
-        info->reserved = 0;
+        info->stats_mode = 0;
     }
     return 0;
 }
@@ -664,7 +717,7 @@ int mtm_mstep(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, d
         info->n_switches = 0;
         info->min_count = h->h_ctrl->min_count;
         info->status = h->h_ctrl->status;
-        info->reserved = 0;
+        info->stats_mode = 0;
     }
     return 0;
 }
@@ -688,8 +741,19 @@ int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, doubl
         info->n_switches = (int64_t)h->h_ctrl->n_switches;
         info->min_count = h->h_ctrl->min_count;
         info->status = h->h_ctrl->status;
-        info->reserved = 0;
+        info->stats_mode = 0;
+        if ((phases & 1) && h->d_cache) {  // how the statistics of this iteration were formed (the call has synchronised)
+            int mode = 0;
+            MTM_CUDA(h, cudaMemcpy(&mode, &h->d_cache->mode, sizeof(int), cudaMemcpyDeviceToHost));
+            info->stats_mode = mode;
+        }
     }
+    return 0;
+}
+
+int mtm_set_delta_stats(mtm_handle *h, int enable) {
+    if (!h) return -1;
+    h->delta_enabled = enable != 0;
     return 0;
 }
 
@@ -799,7 +863,7 @@ int mtm_em_step_host(mtm_handle *h, const double *z_host, const double *x_host, 
         info->n_switches = (int64_t)h->h_ctrl->n_switches;
         info->min_count = h->h_ctrl->min_count;
         info->status = h->h_ctrl->status;
-        info->reserved = 0;
+        info->stats_mode = 0;
     }
     return 0;
 }
@@ -821,6 +885,7 @@ int mtm_em_fit(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *assig
         h->hist_cap = n_steps;
     }
     MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    if (int rc = invalidate_stats_cache(h)) return rc;  // a fit starts from nothing it did not compute itself
     // guard + first M-step (MMM:1328-1337)
     if (int rc = enqueue_stats(h, assign_dev, n_c, 0, 0)) return rc;
     if (int rc = enqueue_finalize(h, n_c, alpha, params_dev, 1, n_steps)) return rc;
@@ -872,7 +937,7 @@ int mtm_mstep_ext(mtm_handle *h, const int32_t *assign_dev, int n_c, double alph
         info->n_switches = 0;
         info->min_count = h->h_ctrl->min_count;
         info->status = h->h_ctrl->status;
-        info->reserved = 0;
+        info->stats_mode = 0;
     }
     return 0;
 }
@@ -896,6 +961,7 @@ int mtm_em_fit_ext(mtm_handle *h, int n_c, double alpha, int n_steps, int32_t *a
         h->hist_cap = n_steps;
     }
     MTM_CUDA(h, cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream));
+    if (int rc = invalidate_stats_cache(h)) return rc;
     MTM_CUDA(h, launch_copy_labels(assign_prev_dev, assign_dev, dt.n, h->d_ctrl, 0, h->stream));
     h->launches += 1;
     // first M-step (SSMM:263): no guard in front of it

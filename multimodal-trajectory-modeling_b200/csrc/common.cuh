@@ -27,6 +27,30 @@ struct Ctrl {
     long long min_count;
 };
 
+// Delta statistics: the reduced (double-double) statistics of the last two label vectors this handle ran a fused
+// E-step on, keyed by a 128-bit hash of the labels.  When the labels an E-step starts from are one of them and few
+// trajectories changed cluster in the iteration before, the fused kernel only visits the trajectories that switch
+// (stats_tile.cuh: stats_delta_warp) and the reduction adds their moments to / subtracts them from the cached sums.
+// Everything is decided on the device (label_hash_kernel, misc.cu): no host round trip, and labels the caller
+// changed behind the library's back simply miss the cache.
+struct StatsCacheEntry {
+    unsigned long long h0, h1;  // label hash
+    long long n;                // trajectories hashed
+    long long sw;               // switches of the E-step that produced these labels
+    unsigned long long stamp;   // age (replacement)
+    int n_c;
+    int valid;
+};
+struct StatsCache {
+    StatsCacheEntry e[2];
+    unsigned long long acc0, acc1;  // hash pass in flight (zero between passes)
+    unsigned long long clock;
+    unsigned int ticket;            // last-block detection of the hash pass
+    int mode;                       // this iteration: 0 = full statistics, 1 = delta against entry `src`
+    int src, dst;                   // entry read / entry written by this iteration's reduction
+    int pad;
+};
+
 struct EStepArgs {
     const double *z;  // (T, n, d) or nullptr
     const double *x;  // (T, n, l)
@@ -49,6 +73,7 @@ struct EStepArgs {
     double *stats_partials;        // nullable: fused mode — the M-step statistics of the NEW labels are
                                    // accumulated in the same pass: (grid, n_c, sstride, 2) block sums
     double pivot[2 * MTM_MAX_DIM]; // fused mode: the moments are taken about this point: z - pivot[0..d), x - pivot[8..8+l)
+    const StatsCache *cache;       // nullable: fused mode may run as delta statistics (cache->mode, block-uniform)
 };
 
 struct StatsArgs {
@@ -110,9 +135,18 @@ size_t stats_smem(int n_c, int d, int l);
 // `scratch` holds kReduceSlices * n_vals * 2 doubles (two-stage fixed-order reduction).
 constexpr int kReduceSlices = 64;
 constexpr int kTail = 4;
+// cache / bases (nullable, R == 1 only): cache->mode == 0: bases[dst] = the reduced (hi, lo) sums; == 1: the block
+// partials are DIFFERENCES, bases[dst] = bases[src] + them; out = bases[dst] rounded.  bases: 2 x n_vals x 2 doubles.
 cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
                                 const Ctrl *ctrl, int check_done, int with_switches, double n_local, int R,
-                                cudaStream_t s);
+                                cudaStream_t s, const StatsCache *cache = nullptr, double *bases = nullptr);
+// 128-bit hash of a label vector + the cache decision of one fused iteration (misc.cu).  role 0 (before the E-step,
+// on the labels it starts from): look the hash up, set cache->mode / src / dst (delta only if allow_delta and the
+// matching entry's switch count is at most n / 8); role 1 (after it, on the new labels): publish entry dst.
+cudaError_t launch_label_hash(const int32_t *assign, int64_t n, int n_c, StatsCache *cache, const Ctrl *ctrl,
+                              int check_done, int role, int allow_delta, int sm_count, cudaStream_t s);
+// shared memory the delta mode of the fused E-step needs inside the statistics region
+size_t stats_delta_smem_bytes(int n_c, int d, int l);
 // tail (nullable) = the kTail trailing slots of the all-reduced statistics buffer
 cudaError_t launch_finalize(const FinalizeArgs &a, const double *tail, cudaStream_t s);
 // per-feature [sum | count] of the finite entries of a (T, n, w) array: out[0..8) sums, out[8..16) counts;

@@ -67,6 +67,7 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     const int r = blockIdx.y;
     Ctrl *const ctrl = a.ctrl + r;
     if (a.check_done && ctrl->done) return;
+    if (a.cache != nullptr && a.cache->mode != 0) return;  // this iteration runs as delta statistics (estep_delta_kernel)
     const double *const params = a.params + (size_t)r * a.n_c * dm.stride();
     int32_t *const assign = a.assign ? a.assign + (size_t)r * a.n : nullptr;
     unsigned long long *const counts = a.counts ? a.counts + (size_t)r * MTM_MAX_CLUSTERS : nullptr;
@@ -240,6 +241,113 @@ __global__ void MTM_E_BOUNDS estep_kernel(const EStepArgs a) {
     }
 }
 
+// Delta-statistics twin of the fused kernel (common.cuh StatsCache, stats_tile.cuh stats_delta_warp): the same
+// E-step and argmax, but instead of the tile-wide statistics pass every warp adds / subtracts the moments of its own
+// trajectories that change cluster.  Launched right after estep_kernel on every fused iteration of a single fit;
+// exactly one of the two does the work (cache->mode, set on the device by the label-hash pass), the other returns
+// at once.  A separate kernel on purpose: any edit inside estep_kernel's tile loop is liable to cost it the
+// uniform-datapath form of its parameter operands (see MTM_E_BOUNDS).
+template <int D_, int L_, bool CONSTP>
+__global__ void MTM_E_BOUNDS estep_delta_kernel(const EStepArgs a) {
+    using DM = Dims<D_, L_>;
+    using PS = PSel<CONSTP>;
+    const DM dm{a.d, a.l};
+    Ctrl *const ctrl = a.ctrl;
+    if (a.check_done && ctrl->done) return;
+    if (a.cache->mode == 0) return;  // full statistics this iteration (estep_kernel)
+    const double *const params = a.params;
+    int32_t *const assign = a.assign;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int stride = dm.stride();
+    double *s_par = reinterpret_cast<double *>(smem_raw);                 // n_c * stride (unused if CONSTP)
+    double *s_logpi = s_par + (CONSTP ? 0 : a.n_c * stride);              // n_c
+    double *s_pi = s_logpi + a.n_c;                                       // n_c
+    uint32_t *s_fin = reinterpret_cast<uint32_t *>(s_pi + a.n_c);         // n_c * T0
+    unsigned int *s_live = s_fin + a.n_c * a.T0;                          // n_c
+    double *const acc_all = reinterpret_cast<double *>(
+        smem_raw + (((reinterpret_cast<unsigned char *>(s_live + a.n_c) - smem_raw) + 15) & ~size_t(15)));
+    const int ss = stats_stride(dm.d(), dm.l());
+    constexpr int NW = kEThreads / 32;
+    int *const s_ent = reinterpret_cast<int *>(acc_all + NW * a.n_c * ss);
+    __shared__ unsigned int s_sw;
+
+    const int tid = threadIdx.x;
+    if (!CONSTP)
+        for (int k = tid; k < a.n_c * stride; k += kEThreads) s_par[k] = params[k];
+    for (int k = tid; k < NW * a.n_c * ss; k += kEThreads) acc_all[k] = 0.0;
+    for (int k = tid; k < ss; k += kEThreads) s_ent[k] = delta_entry(k, dm.d(), dm.l());
+    if (tid == 0) s_sw = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < a.n_c; c0 += kEThreads / 8) {
+        const int c_raw = c0 + (tid >> 3);
+        const bool c_ok = c_raw < a.n_c;
+        const int c = c_ok ? c_raw : a.n_c - 1;
+        const double *row = params + (size_t)c * stride;
+        if (c_ok && (tid & 7) == 0) {
+            const double pi_c = __ldg(row);
+            s_pi[c] = pi_c;
+            s_logpi[c] = log(pi_c);
+        }
+        mean_finite_masks_lanes(dm, row, a.T0, s_fin + c * a.T0, c_ok);
+    }
+    __syncthreads();
+    for (int c = tid; c < a.n_c; c += kEThreads) {
+        uint32_t any = 0;
+        for (int t = 0; t < a.T0; ++t) any |= s_fin[c * a.T0 + t];
+        s_live[c] = any;
+    }
+    __syncthreads();
+
+    const int64_t n = a.n;
+    const int64_t n_tiles = (n + kEThreads - 1) / kEThreads;
+    const int64_t zs = a.ld * dm.d(), xs = a.ld * dm.l();
+    unsigned int sw_acc = 0;
+    int bad = 0;
+    double *const w_acc = acc_all + (tid >> 5) * a.n_c * ss;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i_raw = tile * kEThreads + tid;
+        const bool valid = i_raw < n;
+        const int64_t i = valid ? i_raw : n - 1;
+        const double *z_i = a.z + i * dm.d();
+        const double *x_i = a.x + i * dm.l();
+        double best = 0.0;
+        int arg = 0;
+        for (int c = 0; c < a.n_c; ++c) {
+            const double ll = filter_eval<DM, true>(dm, z_i, zs, x_i, xs, s_live[c] ? a.T0 : 0,
+                                                    PS::get(s_par, c, c, stride), s_fin + c * a.T0, bad, a.tshift);
+            const double lc = s_pi[c] * exp(ll);
+            const bool take = (c == 0) || (!(best != best) && (lc > best || lc != lc));
+            if (take) {
+                best = lc;
+                arg = c;
+            }
+        }
+        int old_lab = arg;
+        if (valid) {
+            old_lab = assign[i];
+            sw_acc += (old_lab != arg) ? 1u : 0u;
+            assign[i] = arg;
+        }
+        stats_delta_warp(dm, a.z, a.x, a.ld, a.T, i, old_lab, arg, valid, a.n_c, w_acc, s_ent, a.pivot);
+    }
+
+    if (bad) atomicOr(&ctrl->status, bad);
+    MTM_UNROLL
+    for (int o = 16; o > 0; o >>= 1) sw_acc += __shfl_xor_sync(0xffffffffu, sw_acc, o);
+    if ((tid & 31) == 0 && sw_acc) atomicAdd(&s_sw, sw_acc);
+    __syncthreads();
+    if (tid == 0 && s_sw) atomicAdd(&ctrl->n_switches, (unsigned long long)s_sw);
+    // the warps' differences, added in warp order, as a (hi, 0) pair per entry: the reduction kernels are shared
+    double *out = a.stats_partials + (size_t)blockIdx.x * 2 * a.n_c * ss;
+    for (int k = tid; k < a.n_c * ss; k += kEThreads) {
+        double s = 0.0;
+        for (int w = 0; w < NW; ++w) s += acc_all[w * a.n_c * ss + k];
+        out[2 * k] = s;
+        out[2 * k + 1] = 0.0;
+    }
+}
+
 // fixed-order sum of the per-block (Q, LL) partials
 __global__ void score_reduce_kernel(const double *__restrict__ partials_all, int grid, double *out_all) {
     const double *partials = partials_all + 2 * (size_t)blockIdx.x * grid;  // one block per restart
@@ -271,6 +379,8 @@ size_t estep_smem(int n_c, int T0, int d, int l, bool fused) {
     return e + (fused ? stats_smem_bytes(n_c, d, l) : 0);
 }
 
+size_t stats_delta_smem_bytes(int n_c, int d, int l) { return stats_delta_bytes(n_c, d, l); }
+
 int estep_grid(int64_t n, int sm_count, bool fused) {
     const int64_t tiles = (n + kEThreads - 1) / kEThreads;
     // Static tile striding (uniform cost per tile), blocks = a multiple of the SM count and of the 3 resident
@@ -300,17 +410,33 @@ static cudaError_t launch_one(const EStepArgs &a, int grid, size_t smem, cudaStr
     return cudaGetLastError();
 }
 
+template <int D_, int L_, bool CONSTP>
+static cudaError_t launch_delta(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
+    auto k = estep_delta_kernel<D_, L_, CONSTP>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, kEThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <int D_, int L_>
 static cudaError_t launch_dl(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {
     const size_t n_par = (size_t)(a.R > 1 ? a.R : 1) * a.n_c * param_stride(a.d, a.l);
+    const bool delta = a.cache != nullptr;  // the twin runs the iteration when the device-side cache says so
     if (D_ > 0 && n_par <= MTM_CONST_DOUBLES) {
         // stage the parameter rows in the constant bank (device -> device, stream ordered)
         cudaError_t e = cudaMemcpyToSymbolAsync(c_par, a.params, n_par * sizeof(double), 0,
                                                 cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
-        return a.z ? launch_one<D_, L_, true, true>(a, grid, smem, s) : launch_one<D_, L_, false, true>(a, grid, smem, s);
+        e = a.z ? launch_one<D_, L_, true, true>(a, grid, smem, s) : launch_one<D_, L_, false, true>(a, grid, smem, s);
+        if (e != cudaSuccess || !delta) return e;
+        return launch_delta<D_, L_, true>(a, grid, smem, s);
     }
-    return a.z ? launch_one<D_, L_, true, false>(a, grid, smem, s) : launch_one<D_, L_, false, false>(a, grid, smem, s);
+    cudaError_t e = a.z ? launch_one<D_, L_, true, false>(a, grid, smem, s) : launch_one<D_, L_, false, false>(a, grid, smem, s);
+    if (e != cudaSuccess || !delta) return e;
+    return launch_delta<D_, L_, false>(a, grid, smem, s);
 }
 
 cudaError_t launch_estep(const EStepArgs &a, int grid, size_t smem, cudaStream_t s) {

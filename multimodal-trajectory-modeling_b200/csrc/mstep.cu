@@ -91,7 +91,8 @@ __global__ void stats_reduce1_kernel(const double *__restrict__ partials_all, in
 }
 
 __global__ void stats_reduce2_kernel(const double *__restrict__ scratch_all, int S, int n_vals, double *out_all,
-                                     const Ctrl *ctrl, int check_done, int with_switches, double n_local) {
+                                     const Ctrl *ctrl, int check_done, int with_switches, double n_local,
+                                     const StatsCache *cache, double *bases) {
     const int r = blockIdx.y;
     if (check_done && ctrl[r].done) return;
     const double *scratch = scratch_all + 2 * (size_t)r * S * n_vals;
@@ -104,6 +105,19 @@ __global__ void stats_reduce2_kernel(const double *__restrict__ scratch_all, int
             const double2 p = *reinterpret_cast<const double2 *>(scratch + 2 * ((size_t)s * n_vals + v));
             dd_add(hi, lo, p.x);
             lo += p.y;
+        }
+        if (cache) {  // statistics cache (single fit): keep the sums of these labels as a (hi, lo) pair
+            double *bd = bases + 2 * ((size_t)cache->dst * n_vals + v);
+            if (cache->mode) {  // the partials were differences against entry src
+                const double *bs = bases + 2 * ((size_t)cache->src * n_vals + v);
+                double bh = bs[0], bl = bs[1];
+                dd_add(bh, bl, hi);
+                bl += lo;
+                hi = bh + bl;
+                lo = bl - (hi - bh);
+            }
+            bd[0] = hi;
+            bd[1] = lo;
         }
         out[v] = hi + lo;
     }
@@ -776,14 +790,14 @@ cudaError_t launch_stats(const StatsArgs &a, int grid, cudaStream_t s) {
 
 cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
                                 const Ctrl *ctrl, int check_done, int with_switches, double n_local, int R,
-                                cudaStream_t s) {
+                                cudaStream_t s, const StatsCache *cache, double *bases) {
     const int threads = 128;
     const int S = grid >= 4 * kReduceSlices ? kReduceSlices : 1;
     const int RR = R > 1 ? R : 1;
     const dim3 g1((n_vals + threads - 1) / threads, S, RR);
     stats_reduce1_kernel<<<g1, threads, 0, s>>>(partials, grid, n_vals, scratch, ctrl, check_done);
     stats_reduce2_kernel<<<dim3(g1.x, RR), threads, 0, s>>>(scratch, S, n_vals, out, ctrl, check_done, with_switches,
-                                                             n_local);
+                                                             n_local, RR == 1 ? cache : nullptr, bases);
     return cudaGetLastError();
 }
 

@@ -282,4 +282,129 @@ __device__ __forceinline__ void stats_tile(const DM &dm, const double *__restric
     }
 }
 
+// ---- delta statistics ---------------------------------------------------------------------------------------------
+// Late EM iterations move few trajectories (1.4 % in the sixth iteration of the 10 M benchmark fit), and the
+// sufficient statistics of the new labels are those of the old ones plus / minus the moments of the movers.  In delta
+// mode (StatsCache, common.cuh) every WARP handles its own movers, one at a time, with the lanes spread over the
+// entries of a cluster's statistics block — no block-wide barrier, no staging, nothing at all for a warp without a
+// mover (64 % of the warps at 1.4 %).  A mover's per-trajectory moments are formed with the very operations of
+// add_moments above (fma over ascending t), so they are bit-identical to what the full pass adds for it; only the
+// order in which trajectories are summed differs, as it does between grids or GPU counts.
+//
+// Step vector of time step t across the lanes: [0, d) z_t - pivot | [8, 8 + l) x_t - pivot | [16, 16 + d) z_{t+1} -
+// pivot; a table entry names the moment group and the two lanes whose product feeds it (lane 32 = the constant 1).
+__host__ __device__ inline int delta_entry(int e, int d, int l) {
+    if (e == 0) return 0;  // cluster size: handled by the caller
+    int o = e - 1;
+    for (int g = 1; g <= 3; ++g) {
+        const int K = g == 1 ? d : (g == 2 ? 2 * d : d + l);
+        const int F = 1 + K + K * (K + 1) / 2;
+        if (o < F) {
+            int a = -1, b = -1;  // -1: the constant 1 (count and plain sums)
+            if (o >= 1 && o <= K) {
+                a = o - 1;
+            } else if (o > K) {
+                int p = o - 1 - K;
+                a = 0;
+                while (p >= K - a) {
+                    p -= K - a;
+                    ++a;
+                }
+                b = a + p;
+            }
+            int la = 32, lb = 32;
+            if (a >= 0) la = a < d ? a : (g == 2 ? 16 + (a - d) : 8 + (a - d));
+            if (b >= 0) lb = b < d ? b : (g == 2 ? 16 + (b - d) : 8 + (b - d));
+            return g | (la << 4) | (lb << 10);
+        }
+        o -= F;
+    }
+    return 0;
+}
+
+// shared memory of the delta mode, carved from the same region as StatsSmem: one plain-double accumulator block per
+// warp (the differences are sums over a handful of trajectories) and the entry table
+__host__ __device__ inline size_t stats_delta_bytes(int n_c, int d, int l) {
+    return (size_t)(kSThreads / 32) * n_c * stats_stride(d, l) * 8 + (size_t)stats_stride(d, l) * 4 + 16;
+}
+
+// One tile, warp by warp; `w_acc` = this warp's accumulators (n_c x sstride), `s_ent` the entry table.
+// Per mover: the rows of eight time steps are requested together (they come from L2: one latency per eight steps,
+// not one per step — the first version, a load per step and per round of entries, spent 17 k cycles per mover), then
+// every lane feeds its entries (one per round of 32) from the step vectors by shuffles.
+template <class DM>
+__device__ __forceinline__ void stats_delta_warp(const DM &dm, const double *__restrict__ z, const double *__restrict__ x,
+                                                 int64_t ld, int T, int64_t i, int old_label, int new_label, bool valid,
+                                                 int n_c, double *w_acc, const int *s_ent, const double *piv) {
+    const unsigned int full = 0xffffffffu;
+    unsigned int movers = __ballot_sync(full, valid && old_label != new_label);
+    if (movers == 0) return;
+    // rounds of 32 entries per statistics block (common.cuh stats_stride, as a constant expression)
+    constexpr int DD = DM::DM, DL = DM::DM + DM::LM;
+    constexpr int RMAX = (1 + (1 + DD + DD * (DD + 1) / 2) + (1 + 2 * DD + DD * (2 * DD + 1)) + (1 + DL + DL * (DL + 1) / 2) + 31) / 32;
+    constexpr int CH = 8;  // time steps in flight
+    const int lane = threadIdx.x & 31;
+    const int d = dm.d(), l = dm.l();
+    const int sstride = stats_stride(d, l);
+    const int64_t zs = ld * d, xs = ld * l;
+    const int sub = lane & 7, grp = lane >> 3;  // 0: z_t, 1: x_t, 2: z_{t+1}
+    const bool has = (grp == 0 && sub < d) || (grp == 1 && sub < l) || (grp == 2 && sub < d);
+    const double pv = has ? piv[(grp == 1 ? MTM_MAX_DIM : 0) + sub] : 0.0;
+    const unsigned int dmask = (1u << d) - 1u, lmask = (1u << l) - 1u;
+    const int shift = grp == 2 ? 1 : 0;
+    const int64_t step = grp == 1 ? xs : zs;
+    int ent[RMAX];
+    MTM_UNROLL
+    for (int r = 0; r < RMAX; ++r) ent[r] = (r * 32 + lane < sstride) ? s_ent[r * 32 + lane] : 0;
+    while (movers) {
+        const int src = __ffs(movers) - 1;
+        movers &= movers - 1;
+        const int64_t j = __shfl_sync(full, i, src);
+        int lo = __shfl_sync(full, old_label, src);
+        const int ln = __shfl_sync(full, new_label, src);
+        if (lo < 0 || lo >= n_c) lo = -1;  // was not counted
+        const double *row = grp == 1 ? x + j * l + sub : z + j * d + sub;
+        double s_r[RMAX];
+        MTM_UNROLL
+        for (int r = 0; r < RMAX; ++r) s_r[r] = 0.0;
+        for (int t0 = 0; t0 < T; t0 += CH) {
+            double v[CH];
+            MTM_UNROLL
+            for (int k = 0; k < CH; ++k) {
+                const int t = t0 + k + shift;
+                v[k] = __longlong_as_double(0x7ff8000000000000LL);
+                if (has && t < T) v[k] = __ldg(row + (int64_t)t * step) - pv;
+            }
+            MTM_UNROLL
+            for (int k = 0; k < CH; ++k) {
+                if (t0 + k < T) {  // warp-uniform
+                    const unsigned int fin = __ballot_sync(full, finite_bits(v[k]));
+                    const bool okz = (fin & dmask) == dmask, okx = ((fin >> 8) & lmask) == lmask,
+                               okn = ((fin >> 16) & dmask) == dmask;
+                    const bool first = t0 + k == 0;
+                    MTM_UNROLL
+                    for (int r = 0; r < RMAX; ++r) {
+                        if (r * 32 < sstride) {  // warp-uniform
+                            const int g = ent[r] & 15, la = (ent[r] >> 4) & 63, lb = (ent[r] >> 10) & 63;
+                            const double va = __shfl_sync(full, v[k], la & 31), vb = __shfl_sync(full, v[k], lb & 31);
+                            const bool cond = g == 1 ? (first && okz) : (g == 2 ? (okz && okn) : (g == 3 && okz && okx));
+                            if (cond) s_r[r] = fma(la == 32 ? 1.0 : va, lb == 32 ? 1.0 : vb, s_r[r]);
+                        }
+                    }
+                }
+            }
+        }
+        MTM_UNROLL
+        for (int r = 0; r < RMAX; ++r) {
+            const int e = r * 32 + lane;
+            if (e < sstride) {
+                const double s = e == 0 ? 1.0 : s_r[r];
+                w_acc[ln * sstride + e] += s;
+                if (lo >= 0) w_acc[lo * sstride + e] -= s;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace mtm

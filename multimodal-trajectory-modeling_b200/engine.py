@@ -390,6 +390,10 @@ class Engine:
         self._chk(self.lib.mtm_fingerprint(self.h, ctypes.byref(st), perm, key))
         return f"{key[0]:016x}{key[1]:016x}"
 
+    def set_delta_stats(self, enable=True):
+        """Delta statistics of the fused EM iteration on / off (mtm_set_delta_stats; default on)."""
+        self._chk(self.lib.mtm_set_delta_stats(self.h, 1 if enable else 0))
+
     def release_workspace(self):
         """Give back the grow-only workspace of pattern_order / kmeans_init (mtm_release_workspace)."""
         self._chk(self.lib.mtm_release_workspace(self.h))

@@ -499,18 +499,28 @@ def test_batched_restarts_equal_sequential(mix, eng):
     batch = torch.from_numpy(a0).to(eng.device)
     P, infos, scores, sstat = eng.sweep_fit(data, batch, n_c, 0.0, n_steps)
     exits = set()
-    for r in range(R):
-        single = torch.from_numpy(a0[r].copy()).to(eng.device)
-        p1, i1 = eng.em_fit(data, single, n_c, 0.0, n_steps)
-        assert i1["exit"] == infos[r]["exit"] and i1["switches"] == infos[r]["switches"], (r, i1, infos[r])
-        assert torch.equal(single, batch[r])
-        exits.add(i1["exit"])
-        if i1["exit"] == "guard0":
-            assert bool(torch.isnan(P[r]).all())
-            continue
-        assert torch.equal(p1, P[r])
-        q, ll, st = eng.score(data, p1, n_c)
-        assert (q, ll) == (scores[r, 0], scores[r, 1]) and st == int(sstat[r])
+    # batched restarts re-sum every cluster in every iteration; a single fit does the same with delta statistics
+    # off (bit-identical then) and differs by rounding with them on (the default)
+    for delta in (False, True):
+        eng.set_delta_stats(delta)
+        try:
+            for r in range(R):
+                single = torch.from_numpy(a0[r].copy()).to(eng.device)
+                p1, i1 = eng.em_fit(data, single, n_c, 0.0, n_steps)
+                assert i1["exit"] == infos[r]["exit"] and i1["switches"] == infos[r]["switches"], (r, i1, infos[r])
+                assert torch.equal(single, batch[r])
+                exits.add(i1["exit"])
+                if i1["exit"] == "guard0":
+                    assert bool(torch.isnan(P[r]).all())
+                    continue
+                if delta:
+                    assert relerr(p1.cpu().numpy(), P[r].cpu().numpy()) < 1e-11
+                    continue
+                assert torch.equal(p1, P[r])
+                q, ll, st = eng.score(data, p1, n_c)
+                assert (q, ll) == (scores[r, 0], scores[r, 1]) and st == int(sstat[r])
+        finally:
+            eng.set_delta_stats(True)
     assert "guard0" in exits and "converged" in exits
     assert len({i["n_e_steps"] for i in infos}) > 2  # restarts really stopped at different iterations
 
@@ -669,6 +679,70 @@ def test_pattern_order(eng):
         assert np.array_equal(ordered.from_resident(r1["probs"]).cpu().numpy(), r0["probs"].cpu().numpy(),
                               equal_nan=True)
         assert np.array_equal(ordered.from_resident(r1["assign"]).cpu().numpy(), r0["assign"].cpu().numpy())
+
+
+@pytest.mark.parametrize("shape", [(60_007, 8, 4, 4, 4), (9_001, 5, 2, 3, 3), (5_003, 4, 3, 5, 2)])
+def test_delta_statistics(eng, shape):
+    """Delta statistics (mtm_b200.h): late EM iterations only visit the trajectories that change cluster.  Stepwise
+    EM through mtm_em_step with the mode on and off: the same switch counts and labels at every iteration,
+    parameters equal to rounding; the mode is really taken once few labels move; a second step from restored labels
+    hits the cache and reproduces the first bit for bit; labels changed behind the library's back miss it."""
+    import ctypes
+
+    import mtm_b200
+    from mtm_b200 import _capi as C
+
+    n, T, d, l, n_c = shape
+    z, x = _synthetic(n, T, d, l, n_c, seed=n % 97, sep=0.6)
+    data = mtm_b200.DeviceData(z, x, eng.device, pattern_order=True)
+    a0 = data.to_resident(np.random.default_rng(3).integers(0, n_c, n).astype(np.int32))
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def step(a, P):
+        info = C.EStepInfo()
+        C.check(eng.lib.mtm_em_step(eng.h, n_c, 0.0, vp(a), vp(P), 3, ctypes.byref(info)), eng.h)
+        return int(info.n_switches), int(info.stats_mode), int(info.status)
+
+    runs = {}
+    try:
+        for enable in (True, False):
+            eng.set_delta_stats(enable)
+            a = a0.clone()
+            P = eng.mstep(data, a, n_c, 0.0)[0]  # binds the set once; the steps below do not re-bind
+            hist = [step(a, P) for _ in range(14)]
+            runs[enable] = (hist, a.clone(), P.clone())
+        eng.set_delta_stats(True)
+        on, off = runs[True], runs[False]
+        assert [h[1] for h in off[0]] == [0] * 14
+        assert [h[0] for h in on[0]] == [h[0] for h in off[0]] and all(h[2] == 0 for h in on[0])
+        modes = [h[1] for h in on[0]]
+        assert modes[0] == 0 and 1 in modes, modes
+        for k in range(1, 14):  # delta exactly when the iteration before moved at most n/8 labels
+            assert modes[k] == (1 if on[0][k - 1][0] * 8 <= n else 0), (k, modes, on[0])
+        assert torch.equal(on[1], off[1])
+        assert relerr(on[2].cpu().numpy(), off[2].cpu().numpy()) < 1e-11
+        # stationary stepping: restore the labels and parameters, step again -> cache hit, same bits
+        a, P = on[1].clone(), on[2].clone()
+        a_keep, P_keep = a.clone(), P.clone()
+        s1 = step(a, P)
+        a1, P1 = a.clone(), P.clone()
+        a.copy_(a_keep)
+        P.copy_(P_keep)
+        s2 = step(a, P)
+        assert s1 == s2 and (s2[1] == 1 or s2[0] * 8 > n)
+        assert torch.equal(a, a1) and torch.equal(P, P1)
+        # labels the caller changed are not in the cache: the iteration sums everything and is right
+        a.copy_(a_keep)
+        P.copy_(P_keep)
+        a[: n // 50] = (a[: n // 50] + 1) % n_c
+        b, Q = a.clone(), P.clone()
+        s3 = step(a, P)
+        assert s3[1] == 0
+        eng.set_delta_stats(False)
+        s4 = step(b, Q)
+        assert s3[0] == s4[0] and torch.equal(a, b) and torch.equal(P, Q)  # both full: identical
+    finally:
+        eng.set_delta_stats(True)
 
 
 def test_pattern_order_workspace(eng):
