@@ -181,7 +181,9 @@ int mtm_mstep(mtm_handle *h, const int32_t *assign_dev, int n_c, double alpha, d
  * as in the full pass, so the two modes differ only in the order trajectories are added (as grids and GPU counts
  * do): same labels, parameters equal to rounding.  The cache is dropped by every mtm_set_data (re-bind after
  * changing the resident buffers in place), by a new pivot and at the start of mtm_em_fit.
- * mtm_set_delta_stats(h, 0) turns the mode off (every iteration sums everything); default on. */
+ * mtm_set_delta_stats(h, mode): 0 = off (every iteration sums everything, no label hashes), 1 = automatic (default:
+ * on unless the set is so small — n n_c < 2e6 — that the iteration is bound by launch latency and three more small
+ * launches cost more than they save), 2 = on for every size.  Drops the cache. */
 int mtm_set_delta_stats(mtm_handle *h, int enable);
 int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, double *params_dev, int phases,
                 mtm_estep_info *info);

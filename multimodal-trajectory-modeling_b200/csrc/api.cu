@@ -119,7 +119,7 @@ struct mtm_handle {
     StatsCache *d_cache = nullptr;
     double *d_bases = nullptr;  // 2 entries x n_vals x (hi, lo)
     size_t bases_cap = 0;
-    bool delta_enabled = true;
+    int delta_mode = 1;  // mtm_set_delta_stats: 0 off, 1 on where it pays (not for launch-bound sizes), 2 always
     std::string err;
     int64_t launches = 0;
 };
@@ -269,6 +269,10 @@ int invalidate_stats_cache(mtm_handle *h) {
 int stats_cache_for(mtm_handle *h, int n_c, StatsCache **out) {
     *out = nullptr;
     const mtm_data &dt = h->data;
+    if (h->delta_mode == 0) return 0;
+    // small sets are launch-latency bound (see the batch size of mtm_em_fit): three more launches per iteration cost
+    // more than the statistics pass they could save
+    if (h->delta_mode == 1 && (double)dt.n * n_c < 2e6) return 0;
     if (stats_delta_smem_bytes(n_c, dt.d, dt.l) > estep_smem(n_c, dt.T, dt.d, dt.l, true) - estep_smem(n_c, dt.T, dt.d, dt.l, false))
         return 0;  // the per-warp accumulators do not fit the fused kernel's statistics region
     if (!h->d_cache) {
@@ -397,8 +401,7 @@ int enqueue_e_and_stats(mtm_handle *h, int n_c, const double *params, int32_t *a
         if (R == 1)
             if (int rc = stats_cache_for(h, n_c, &cache)) return rc;
         if (cache) {
-            MTM_CUDA(h, launch_label_hash(assign, dt.n, n_c, cache, h->d_ctrl, check_done, 0, h->delta_enabled ? 1 : 0,
-                                          h->sm_count, h->stream));
+            MTM_CUDA(h, launch_label_hash(assign, dt.n, n_c, cache, h->d_ctrl, check_done, 0, 1, h->sm_count, h->stream));
             h->launches += 1;
         }
         int grid = 0;
@@ -753,8 +756,10 @@ int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, doubl
 
 int mtm_set_delta_stats(mtm_handle *h, int enable) {
     if (!h) return -1;
-    h->delta_enabled = enable != 0;
-    return 0;
+    if (enable < 0 || enable > 2) return fail(h, -1, "mtm_set_delta_stats: 0 (off), 1 (automatic) or 2 (always)");
+    h->delta_mode = enable;
+    DeviceGuard g(h->device);
+    return invalidate_stats_cache(h);
 }
 
 int mtm_em_step_host(mtm_handle *h, const double *z_host, const double *x_host, int T, int64_t n, int d, int l,

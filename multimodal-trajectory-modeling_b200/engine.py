@@ -390,9 +390,10 @@ class Engine:
         self._chk(self.lib.mtm_fingerprint(self.h, ctypes.byref(st), perm, key))
         return f"{key[0]:016x}{key[1]:016x}"
 
-    def set_delta_stats(self, enable=True):
-        """Delta statistics of the fused EM iteration on / off (mtm_set_delta_stats; default on)."""
-        self._chk(self.lib.mtm_set_delta_stats(self.h, 1 if enable else 0))
+    def set_delta_stats(self, mode=1):
+        """Delta statistics of the fused EM iteration (mtm_set_delta_stats): 0 / False off, 1 / True automatic
+        (the default: on unless the set is launch-latency bound), 2 on for every size."""
+        self._chk(self.lib.mtm_set_delta_stats(self.h, int(mode)))
 
     def release_workspace(self):
         """Give back the grow-only workspace of pattern_order / kmeans_init (mtm_release_workspace)."""

@@ -79,8 +79,17 @@ def test_loglik_golden(g_ssm, eng):
         assert relerr(llx, g(f"s{k}_llx")) < RTOL, (T, d, l)
 
 
+@pytest.fixture(params=[1, 2], ids=["stats-auto", "stats-delta"])
+def delta_mode(request, eng):
+    """The golden fits run twice: as shipped (these sets are small, so every iteration re-sums every cluster) and
+    with delta statistics forced on (mtm_set_delta_stats 2) — the reference's traces must come out either way."""
+    eng.set_delta_stats(request.param)
+    yield request.param
+    eng.set_delta_stats(1)
+
+
 @pytest.mark.parametrize("key", ["c2s", "c3s", "slow", "adnish", "mmmtest", "oned", "short", "guardexit"])
-def test_em_trace(g_em, mix, key):
+def test_em_trace(g_em, mix, key, delta_mode):
     c = _case(g_em, key)
     mdl = mix.MMLinGaussSS_marginalizable(n_clusters=c["n_c"], states=c["z"], observations=c["x"],
                                           random_seed=c["seed"], alpha=c["alpha"])
@@ -502,7 +511,7 @@ def test_batched_restarts_equal_sequential(mix, eng):
     # batched restarts re-sum every cluster in every iteration; a single fit does the same with delta statistics
     # off (bit-identical then) and differs by rounding with them on (the default)
     for delta in (False, True):
-        eng.set_delta_stats(delta)
+        eng.set_delta_stats(2 if delta else 0)
         try:
             for r in range(R):
                 single = torch.from_numpy(a0[r].copy()).to(eng.device)
@@ -520,7 +529,7 @@ def test_batched_restarts_equal_sequential(mix, eng):
                 q, ll, st = eng.score(data, p1, n_c)
                 assert (q, ll) == (scores[r, 0], scores[r, 1]) and st == int(sstat[r])
         finally:
-            eng.set_delta_stats(True)
+            eng.set_delta_stats(1)
     assert "guard0" in exits and "converged" in exits
     assert len({i["n_e_steps"] for i in infos}) > 2  # restarts really stopped at different iterations
 
@@ -705,13 +714,12 @@ def test_delta_statistics(eng, shape):
 
     runs = {}
     try:
-        for enable in (True, False):
-            eng.set_delta_stats(enable)
+        for enable in (False, True):  # (changing the mode drops the cache: the delta run goes last and leaves it warm)
+            eng.set_delta_stats(2 if enable else 0)  # 2: also for sets this small
             a = a0.clone()
             P = eng.mstep(data, a, n_c, 0.0)[0]  # binds the set once; the steps below do not re-bind
             hist = [step(a, P) for _ in range(14)]
             runs[enable] = (hist, a.clone(), P.clone())
-        eng.set_delta_stats(True)
         on, off = runs[True], runs[False]
         assert [h[1] for h in off[0]] == [0] * 14
         assert [h[0] for h in on[0]] == [h[0] for h in off[0]] and all(h[2] == 0 for h in on[0])
@@ -738,11 +746,11 @@ def test_delta_statistics(eng, shape):
         b, Q = a.clone(), P.clone()
         s3 = step(a, P)
         assert s3[1] == 0
-        eng.set_delta_stats(False)
+        eng.set_delta_stats(0)
         s4 = step(b, Q)
         assert s3[0] == s4[0] and torch.equal(a, b) and torch.equal(P, Q)  # both full: identical
     finally:
-        eng.set_delta_stats(True)
+        eng.set_delta_stats(1)
 
 
 def test_pattern_order_workspace(eng):
