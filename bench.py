@@ -576,19 +576,23 @@ def leg_em(ctx, cfg, steps, warmup, tag, pattern_order=True):
     # how the M-step statistics of the timed iteration were formed (mtm_b200.h, "delta statistics": late iterations
     # move few trajectories and only those are visited), and the same iteration with the mode switched off
     k_full = max(1, min(steps, 5))
+    assign_default, params_default = run.assign.clone(), run.params.clone()  # the timed iteration as shipped
     ctx.eng.set_delta_stats(False)
     run.restore()
     run.phase(3)
     full_total, full_e, _ = run.timed_steps(k_full)
     chk_full = run.check(n_total)
     params_full = run.params.clone()
-    ctx.eng.set_delta_stats(True)
-    run.check(n_total)  # leaves the runner in the state after the timed iteration, formed the default way
+    labels_same = bool(ctx.torch.equal(run.assign, assign_default))
+    ctx.eng.set_delta_stats(True)  # (drops the cache)
+    run.assign.copy_(assign_default)  # the runner goes on in the state the default iteration left
+    run.params.copy_(params_default)
     statistics = {"mode_of_timed_iteration": "delta" if chk["stats_mode"] == 1 else "full",
                   "switch_fraction": chk["n_switches"] / n_total,
                   "ms_per_step_full_statistics": full_total / k_full, "kernel_ms_full_statistics": full_e,
                   "steps_full_statistics": k_full, "mode_when_switched_off": chk_full["stats_mode"],
-                  "params_max_rel_err_delta_vs_full": rel_err(run.params.cpu().numpy(), params_full.cpu().numpy()),
+                  "labels_equal_delta_vs_full": labels_same,
+                  "params_max_rel_err_delta_vs_full": rel_err(params_default.cpu().numpy(), params_full.cpu().numpy()),
                   "note": "value / ms_per_step are the iteration as mtm_em_step and mtm_em_fit run it (delta statistics "
                           "when the previous iteration moved at most n/8 labels); the *_full_statistics fields time the "
                           "same iteration with every cluster re-summed from all members, as the reference's M_step does"}

@@ -202,7 +202,7 @@ bool can_fuse(const mtm_data *dt, int n_c) {
 int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n_c, int T0, int32_t *assign,
                   int count_switches, double *ll, double *probs, double *prenorm, unsigned long long *counts,
                   double *score_partials, int check_done, int *grid_out, bool fused = false, int R = 1,
-                  const StatsCache *cache = nullptr) {
+                  StatsCache *cache = nullptr) {
     EStepArgs a{};
     a.z = dt->z_dev;
     a.x = dt->x_dev;
@@ -233,6 +233,7 @@ int enqueue_estep(mtm_handle *h, const mtm_data *dt, const double *params, int n
         a.stats_partials = h->d_partials;
         memcpy(a.pivot, h->pivot, sizeof(a.pivot));  // valid: the callers of the fused mode ran ensure_pivot
         a.cache = (R == 1) ? cache : nullptr;
+        a.delta_grid = estep_delta_grid(dt->n, h->sm_count);
     }
     const size_t smem = estep_smem(n_c, a.T0, a.d, a.l, fused);
     if (smem > 200 * 1024) return fail(h, -1, "E-step shared memory %zu B too large (n_c * T0 too big)", smem);
@@ -352,7 +353,8 @@ int enqueue_stats_reduce(mtm_handle *h, int n_c, int grid, int check_done, int w
     if (int rc = ensure(h, h->d_statsbuf, h->statsbuf_cap, ((size_t)n_vals + kTail) * R)) return rc;
     MTM_CUDA(h, launch_stats_reduce(h->d_partials, grid, n_vals, h->d_statsbuf,
                                     h->d_partials + 2 * (size_t)R * grid * n_vals, h->d_ctrl, check_done,
-                                    with_switches, (double)dt.n, R, h->stream, cache, h->d_bases));
+                                    with_switches, (double)dt.n, R, h->stream, cache, h->d_bases,
+                                    estep_delta_grid(dt.n, h->sm_count)));
     h->launches += 2;
     return allreduce_stats(h, h->d_statsbuf, ((size_t)n_vals + kTail) * R, R);
 }

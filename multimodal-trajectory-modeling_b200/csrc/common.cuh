@@ -48,7 +48,7 @@ struct StatsCache {
     unsigned int ticket;            // last-block detection of the hash pass
     int mode;                       // this iteration: 0 = full statistics, 1 = delta against entry `src`
     int src, dst;                   // entry read / entry written by this iteration's reduction
-    int pad;
+    unsigned int next_chunk;        // work counter of estep_delta_kernel (32-trajectory chunks), zeroed by the pre pass
 };
 
 struct EStepArgs {
@@ -73,7 +73,8 @@ struct EStepArgs {
     double *stats_partials;        // nullable: fused mode — the M-step statistics of the NEW labels are
                                    // accumulated in the same pass: (grid, n_c, sstride, 2) block sums
     double pivot[2 * MTM_MAX_DIM]; // fused mode: the moments are taken about this point: z - pivot[0..d), x - pivot[8..8+l)
-    const StatsCache *cache;       // nullable: fused mode may run as delta statistics (cache->mode, block-uniform)
+    StatsCache *cache;             // nullable: fused mode may run as delta statistics (cache->mode, block-uniform)
+    int delta_grid;                // blocks of the delta twin
 };
 
 struct StatsArgs {
@@ -136,10 +137,14 @@ size_t stats_smem(int n_c, int d, int l);
 constexpr int kReduceSlices = 64;
 constexpr int kTail = 4;
 // cache / bases (nullable, R == 1 only): cache->mode == 0: bases[dst] = the reduced (hi, lo) sums; == 1: the block
-// partials are DIFFERENCES, bases[dst] = bases[src] + them; out = bases[dst] rounded.  bases: 2 x n_vals x 2 doubles.
+// partials are DIFFERENCES (from grid_delta blocks), bases[dst] = bases[src] + them; out = bases[dst] rounded.
+// bases: 2 x n_vals x 2 doubles.
 cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
                                 const Ctrl *ctrl, int check_done, int with_switches, double n_local, int R,
-                                cudaStream_t s, const StatsCache *cache = nullptr, double *bases = nullptr);
+                                cudaStream_t s, const StatsCache *cache = nullptr, double *bases = nullptr,
+                                int grid_delta = 0);
+// blocks of estep_delta_kernel: one wave (the kernel hands out 32-trajectory chunks from a counter)
+int estep_delta_grid(int64_t n, int sm_count);
 // 128-bit hash of a label vector + the cache decision of one fused iteration (misc.cu).  role 0 (before the E-step,
 // on the labels it starts from): look the hash up, set cache->mode / src / dst (delta only if allow_delta and the
 // matching entry's switch count is at most n / 8); role 1 (after it, on the new labels): publish entry dst.

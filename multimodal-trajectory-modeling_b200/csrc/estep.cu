@@ -269,13 +269,14 @@ __global__ void MTM_E_BOUNDS estep_delta_kernel(const EStepArgs a) {
         smem_raw + (((reinterpret_cast<unsigned char *>(s_live + a.n_c) - smem_raw) + 15) & ~size_t(15)));
     const int ss = stats_stride(dm.d(), dm.l());
     constexpr int NW = kEThreads / 32;
-    int *const s_ent = reinterpret_cast<int *>(acc_all + NW * a.n_c * ss);
+    const int nv = 2 * a.n_c * ss;  // (hi, lo) pairs of one accumulator block
+    int *const s_ent = reinterpret_cast<int *>(acc_all + NW * nv);
     __shared__ unsigned int s_sw;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (!CONSTP)
         for (int k = tid; k < a.n_c * stride; k += kEThreads) s_par[k] = params[k];
-    for (int k = tid; k < NW * a.n_c * ss; k += kEThreads) acc_all[k] = 0.0;
+    for (int k = tid; k < NW * nv; k += kEThreads) acc_all[k] = 0.0;
     for (int k = tid; k < ss; k += kEThreads) s_ent[k] = delta_entry(k, dm.d(), dm.l());
     if (tid == 0) s_sw = 0;
     __syncthreads();
@@ -299,14 +300,22 @@ __global__ void MTM_E_BOUNDS estep_delta_kernel(const EStepArgs a) {
     }
     __syncthreads();
 
+    // Work distribution: every WARP draws 32-trajectory chunks from one counter (zeroed by the label-hash pass that
+    // selected this kernel).  The tile loop of this kernel has no block-wide barrier, so warps run free; one wave of
+    // blocks then carries the whole launch with one prologue each and no tail — with estep_kernel's static striding
+    // a 1.25 M shard (one rank of eight) paid 8 % for 12 rounds of block prologues or, with few blocks, for imbalance.
     const int64_t n = a.n;
-    const int64_t n_tiles = (n + kEThreads - 1) / kEThreads;
+    const unsigned int n_chunks = (unsigned int)((n + 31) / 32);
     const int64_t zs = a.ld * dm.d(), xs = a.ld * dm.l();
     unsigned int sw_acc = 0;
     int bad = 0;
-    double *const w_acc = acc_all + (tid >> 5) * a.n_c * ss;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i_raw = tile * kEThreads + tid;
+    double *const w_acc = acc_all + (tid >> 5) * nv;
+    for (;;) {
+        unsigned int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&a.cache->next_chunk, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= n_chunks) break;
+        const int64_t i_raw = (int64_t)chunk * 32 + lane;
         const bool valid = i_raw < n;
         const int64_t i = valid ? i_raw : n - 1;
         const double *z_i = a.z + i * dm.d();
@@ -335,16 +344,19 @@ __global__ void MTM_E_BOUNDS estep_delta_kernel(const EStepArgs a) {
     if (bad) atomicOr(&ctrl->status, bad);
     MTM_UNROLL
     for (int o = 16; o > 0; o >>= 1) sw_acc += __shfl_xor_sync(0xffffffffu, sw_acc, o);
-    if ((tid & 31) == 0 && sw_acc) atomicAdd(&s_sw, sw_acc);
+    if (lane == 0 && sw_acc) atomicAdd(&s_sw, sw_acc);
     __syncthreads();
     if (tid == 0 && s_sw) atomicAdd(&ctrl->n_switches, (unsigned long long)s_sw);
-    // the warps' differences, added in warp order, as a (hi, 0) pair per entry: the reduction kernels are shared
-    double *out = a.stats_partials + (size_t)blockIdx.x * 2 * a.n_c * ss;
-    for (int k = tid; k < a.n_c * ss; k += kEThreads) {
-        double s = 0.0;
-        for (int w = 0; w < NW; ++w) s += acc_all[w * a.n_c * ss + k];
-        out[2 * k] = s;
-        out[2 * k + 1] = 0.0;
+    // the warps' differences, added in warp order; the reduction kernels are shared with the full pass
+    double *out = a.stats_partials + (size_t)blockIdx.x * nv;
+    for (int k = tid; k < nv / 2; k += kEThreads) {
+        double hi = 0.0, lo = 0.0;
+        for (int w = 0; w < NW; ++w) {
+            dd_add(hi, lo, acc_all[w * nv + 2 * k]);
+            lo += acc_all[w * nv + 2 * k + 1];
+        }
+        out[2 * k] = hi;
+        out[2 * k + 1] = lo;
     }
 }
 
@@ -380,6 +392,14 @@ size_t estep_smem(int n_c, int T0, int d, int l, bool fused) {
 }
 
 size_t stats_delta_smem_bytes(int n_c, int d, int l) { return stats_delta_bytes(n_c, d, l); }
+
+int estep_delta_grid(int64_t n, int sm_count) {
+    // one wave of the 3 blocks per SM that fit (148 registers x 128 threads); any other grid works too, the chunks
+    // are drawn from a counter
+    const int64_t blocks = (n + kEThreads - 1) / kEThreads;
+    const int64_t cap = (int64_t)sm_count * 3;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
 
 int estep_grid(int64_t n, int sm_count, bool fused) {
     const int64_t tiles = (n + kEThreads - 1) / kEThreads;
@@ -417,7 +437,7 @@ static cudaError_t launch_delta(const EStepArgs &a, int grid, size_t smem, cudaS
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k<<<grid, kEThreads, smem, s>>>(a);
+    k<<<a.delta_grid, kEThreads, smem, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -76,12 +76,21 @@ __global__ void __launch_bounds__(256) label_hash_kernel(const int32_t *__restri
         h0 += __shfl_xor_sync(0xffffffffu, h0, o);
         h1 += __shfl_xor_sync(0xffffffffu, h1, o);
     }
+    // one pair of atomics per BLOCK: thousands of same-address atomics serialise in L2 (19 us at 1.25 M labels with
+    // one pair per warp)
+    __shared__ unsigned long long s_h[2][8];
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&cache->acc0, h0);
-        atomicAdd(&cache->acc1, h1);
+        s_h[0][threadIdx.x >> 5] = h0;
+        s_h[1][threadIdx.x >> 5] = h1;
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
+    for (int w = 1; w < 8; ++w) {
+        h0 += s_h[0][w];
+        h1 += s_h[1][w];
+    }
+    atomicAdd(&cache->acc0, h0);
+    atomicAdd(&cache->acc1, h1);
     __threadfence();
     if (atomicAdd(&cache->ticket, 1u) != gridDim.x - 1) return;
     __threadfence();
@@ -104,6 +113,7 @@ __global__ void __launch_bounds__(256) label_hash_kernel(const int32_t *__restri
         cache->mode = mode;
         cache->src = src;
         cache->dst = dst;
+        cache->next_chunk = 0;
     } else {
         StatsCacheEntry &e = cache->e[cache->dst];
         e.h0 = a0;
@@ -121,8 +131,8 @@ __global__ void __launch_bounds__(256) label_hash_kernel(const int32_t *__restri
 
 cudaError_t launch_label_hash(const int32_t *assign, int64_t n, int n_c, StatsCache *cache, const Ctrl *ctrl,
                               int check_done, int role, int allow_delta, int sm_count, cudaStream_t s) {
-    int grid = (int)((n + 1023) / 1024);  // about four labels per thread
-    if (grid > sm_count * 8) grid = sm_count * 8;
+    int grid = (int)((n + 2047) / 2048);  // at least eight labels per thread
+    if (grid > sm_count * 4) grid = sm_count * 4;
     if (grid < 1) grid = 1;
     label_hash_kernel<<<grid, 256, 0, s>>>(assign, n, n_c, cache, ctrl, check_done, role, allow_delta);
     return cudaGetLastError();

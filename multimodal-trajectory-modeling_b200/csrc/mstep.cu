@@ -58,9 +58,11 @@ __global__ void __launch_bounds__(kSThreads) stats_kernel(const StatsArgs a) {
 // tail slots (kTail, common.cuh): out[n_vals] = n_switches of the preceding E-step (exact integer as double),
 //             out[n_vals+1] = local n, out[n_vals+2..3] = this rank's NONFINITE / SINGULAR flags (0 or 1)
 __global__ void stats_reduce1_kernel(const double *__restrict__ partials_all, int grid, int n_vals,
-                                     double *scratch_all, const Ctrl *ctrl, int check_done) {
+                                     double *scratch_all, const Ctrl *ctrl, int check_done, const StatsCache *cache,
+                                     int grid_delta) {
     const int r = blockIdx.z;  // batched restarts
     if (check_done && ctrl[r].done) return;
+    if (cache && cache->mode) grid = grid_delta;  // the delta twin wrote the partials: one wave of blocks
     const double *partials = partials_all + 2 * (size_t)r * grid * n_vals;
     double *scratch = scratch_all + 2 * (size_t)r * gridDim.y * n_vals;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -790,12 +792,13 @@ cudaError_t launch_stats(const StatsArgs &a, int grid, cudaStream_t s) {
 
 cudaError_t launch_stats_reduce(const double *partials, int grid, int n_vals, double *out, double *scratch,
                                 const Ctrl *ctrl, int check_done, int with_switches, double n_local, int R,
-                                cudaStream_t s, const StatsCache *cache, double *bases) {
+                                cudaStream_t s, const StatsCache *cache, double *bases, int grid_delta) {
     const int threads = 128;
     const int S = grid >= 4 * kReduceSlices ? kReduceSlices : 1;
     const int RR = R > 1 ? R : 1;
     const dim3 g1((n_vals + threads - 1) / threads, S, RR);
-    stats_reduce1_kernel<<<g1, threads, 0, s>>>(partials, grid, n_vals, scratch, ctrl, check_done);
+    stats_reduce1_kernel<<<g1, threads, 0, s>>>(partials, grid, n_vals, scratch, ctrl, check_done,
+                                                RR == 1 ? cache : nullptr, grid_delta);
     stats_reduce2_kernel<<<dim3(g1.x, RR), threads, 0, s>>>(scratch, S, n_vals, out, ctrl, check_done, with_switches,
                                                              n_local, RR == 1 ? cache : nullptr, bases);
     return cudaGetLastError();

@@ -322,13 +322,15 @@ __host__ __device__ inline int delta_entry(int e, int d, int l) {
     return 0;
 }
 
-// shared memory of the delta mode, carved from the same region as StatsSmem: one plain-double accumulator block per
-// warp (the differences are sums over a handful of trajectories) and the entry table
+// shared memory of the delta mode, carved from the same region as StatsSmem: one (hi, lo) accumulator block per warp
+// and the entry table.  Double-double although the differences are sums over a handful of trajectories: the delta
+// kernel hands its chunks out dynamically, so WHICH warp adds a mover varies from run to run, and with ~106-bit sums
+// the rounded result does not (short of a sum landing within 2^-106 of a rounding boundary).
 __host__ __device__ inline size_t stats_delta_bytes(int n_c, int d, int l) {
-    return (size_t)(kSThreads / 32) * n_c * stats_stride(d, l) * 8 + (size_t)stats_stride(d, l) * 4 + 16;
+    return (size_t)(kSThreads / 32) * n_c * stats_stride(d, l) * 16 + (size_t)stats_stride(d, l) * 4 + 16;
 }
 
-// One tile, warp by warp; `w_acc` = this warp's accumulators (n_c x sstride), `s_ent` the entry table.
+// One chunk of 32 trajectories; `w_acc` = this warp's accumulators (n_c x sstride x (hi, lo)), `s_ent` the entry table.
 // Per mover: the rows of eight time steps are requested together (they come from L2: one latency per eight steps,
 // not one per step — the first version, a load per step and per round of entries, spent 17 k cycles per mover), then
 // every lane feeds its entries (one per round of 32) from the step vectors by shuffles.
@@ -399,8 +401,12 @@ __device__ __forceinline__ void stats_delta_warp(const DM &dm, const double *__r
             const int e = r * 32 + lane;
             if (e < sstride) {
                 const double s = e == 0 ? 1.0 : s_r[r];
-                w_acc[ln * sstride + e] += s;
-                if (lo >= 0) w_acc[lo * sstride + e] -= s;
+                double *an = w_acc + 2 * (ln * sstride + e);
+                dd_add(an[0], an[1], s);
+                if (lo >= 0) {
+                    double *ao = w_acc + 2 * (lo * sstride + e);
+                    dd_add(ao[0], ao[1], -s);
+                }
             }
         }
         __syncwarp();

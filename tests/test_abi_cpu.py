@@ -123,7 +123,8 @@ def test_headline_kernel_keeps_uniform_parameter_operands():
     assert re.search(r"DFMA R\d+, R\d+(\.reuse)?, UR\d+, R", sass), "no uniform-register DFMA operands"
     # both (4, 4) kernels (joint and observation-only): the parameter bank c[0x3] is read through the uniform
     # datapath (LDCU.64 UR, c[0x3][UR+imm]); the fallback form reads it with LDC.64 R, c[0x3][R+imm]
-    for kern in ("ILi4ELi4ELb1ELb1E", "ILi4ELi4ELb0ELb1E"):
+    # ... and the delta-statistics twin of the joint kernel (estep_delta_kernel<4, 4, CONSTP>)
+    for kern in ("estep_kernelILi4ELi4ELb1ELb1E", "estep_kernelILi4ELi4ELb0ELb1E", "estep_delta_kernelILi4ELi4ELb1E"):
         body = next(b for b in re.split(r"\n\s*Function : ", sass) if kern in b.split("\n")[0])
         n_u = len(re.findall(r"LDCU\.64 UR\d+, c\[0x3\]", body))
         n_v = len(re.findall(r"LDC\.64 R\d+, c\[0x3\]", body))
