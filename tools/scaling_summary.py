@@ -14,7 +14,8 @@ def main():
           f"(T=8, d=l=4, n_c=8, 20 % missing)")
     print("# columns: N | ms per EM iteration | evaluations/s | efficiency v_N/(N v_1) | roofline.frac (algorithmic "
           "flops / measured DFMA peak) | e2e ms per step | H2D GB/s per rank (min) | per-fit ms (first call of the "
-          "process) | C1 s | C2 ms | C4 ms | C5 s | replay on one GPU: labels equal, max rel param err | class gate\n")
+          "process) | C1 s | C2 ms | C4 ms | C5 s | replay on one GPU: labels equal, max rel param err | class gate | "
+          "M-step statistics of the timed iteration | the same iteration with every cluster re-summed, ms\n")
     v1 = None
     for N in (1, 2, 4, 8):
         path = os.path.join(ROOT, "profiles", f"{tag}_bench_n{N}.json")
@@ -32,7 +33,8 @@ def main():
               f"({pf['ms_total_first_call']:.1f}) | {c['C1']['seconds']:.3f} | {c['C2']['ms_per_step']:.3f} | "
               f"{c['C4']['ms']:.1f} | {c['C5']['seconds_per_sweep_iteration']:.3f} | "
               + (f"{rp['assignments_equal']}, {rp['params_max_rel_err']:.1e}" if rp else "-")
-              + f" | {cg['ok'] if cg else '-'}")
+              + f" | {cg['ok'] if cg else '-'}"
+              + f" | {d['statistics']['mode_of_timed_iteration']} | {d['statistics']['ms_per_step_full_statistics']:.3f}")
         st, wc, ck = d["state"], d["workload_check"], d["clocks"]
         print(f"    state: sha256(labels)={str(st.get('assign_sha256'))[:16]} Q={st.get('Q'):.6f} "
               f"min_count={wc.get('min_count')} status={wc.get('status')} invalid={d.get('invalid')} "
