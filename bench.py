@@ -523,6 +523,10 @@ def em_roofline(ctx, cfg, ds, n_loc, ms_e, ms_m, pattern_order, kernel, wsc, del
     return {"bound": "fp64", "achieved": tf, "peak": ctx.fp64_peak, "unit": "TFLOP/s", "frac": tf / ctx.fp64_peak,
             "traffic": (5.168793e9 + 112.147968e6) if captured else None,
             "traffic_unit": "bytes per launch (ncu capture of this configuration)" if captured else None,
+            "traffic_note": ("no ncu capture of the final delta twin (GPU budget of the round); its static-striding build "
+                             "read 5.1626 GB and wrote 114.1 MB per launch at this size (profiles/r2_delta_ncu_summary.md), "
+                             "of which 72 MB were block partials that the final one-wave grid cuts to 6 MB")
+            if (delta and n_loc == 10_000_000 and (T, d, l, n_c) == (8, 4, 4, 8) and pattern_order) else None,
             "algorithmic_bytes": bpt * n_loc, "kernel": kernel, "kernel_ms": ms_e, "flops_per_eval": f_eval,
             "evals_per_launch": evals,
             # What the kernel EXECUTES: FP64 instructions per evaluation by code path (SASS counts of the time loop:
