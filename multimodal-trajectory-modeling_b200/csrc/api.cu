@@ -120,6 +120,7 @@ struct mtm_handle {
     double *d_bases = nullptr;  // 2 entries x n_vals x (hi, lo)
     size_t bases_cap = 0;
     int delta_mode = 1;  // mtm_set_delta_stats: 0 off, 1 on where it pays (not for launch-bound sizes), 2 always
+    bool cache_in_use = false;  // the last fused iteration went through the statistics cache
     std::string err;
     int64_t launches = 0;
 };
@@ -402,6 +403,7 @@ int enqueue_e_and_stats(mtm_handle *h, int n_c, const double *params, int32_t *a
         StatsCache *cache = nullptr;
         if (R == 1)
             if (int rc = stats_cache_for(h, n_c, &cache)) return rc;
+        h->cache_in_use = cache != nullptr;
         if (cache) {
             MTM_CUDA(h, launch_label_hash(assign, dt.n, n_c, cache, h->d_ctrl, check_done, 0, 1, h->sm_count, h->stream));
             h->launches += 1;
@@ -747,7 +749,7 @@ int mtm_em_step(mtm_handle *h, int n_c, double alpha, int32_t *assign_dev, doubl
         info->min_count = h->h_ctrl->min_count;
         info->status = h->h_ctrl->status;
         info->stats_mode = 0;
-        if ((phases & 1) && h->d_cache) {  // how the statistics of this iteration were formed (the call has synchronised)
+        if ((phases & 1) && h->d_cache && h->cache_in_use) {  // how this iteration's statistics were formed (the call has synchronised)
             int mode = 0;
             MTM_CUDA(h, cudaMemcpy(&mode, &h->d_cache->mode, sizeof(int), cudaMemcpyDeviceToHost));
             info->stats_mode = mode;
