@@ -136,7 +136,7 @@ int orc_dense_loglik(const double *Y, long n, int K, const double *mean, const d
                 out[i] = NAN;
                 continue;
             }
-            memcpy(sol, r, sizeof(double) * k);
+            for (int a = 0; a < k; ++a) sol[a] = r[a];
             lu_solve(sub2, k, piv, sol);
             for (int a = 0; a < k; ++a) q += r[a] * sol[a];
             out[i] = -0.5 * log(pow(2.0 * M_PI, (double)k) * det) - 0.5 * q;
